@@ -1,0 +1,208 @@
+"""Generates tests/golden/*.npz by executing the UNMODIFIED reference (/root/reference/bask,
+loaded through oracle/ref_loader.py) together with the installed scikit-learn.
+
+Run in the build container only (the reference tree does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+Every array is float64 unless noted.  What each file pins is listed in tests/golden/README.md.
+"""
+import os
+import sys
+import time
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, REPO)
+
+from oracle.ref_loader import load_reference  # noqa: E402
+
+bask = load_reference()
+from bask.acquisition import (LCB, PVRS, Expectation, ExpectedImprovement,  # noqa: E402
+                              MaxValueSearch, ThompsonSampling, TopTwoEI, VarianceReduction,
+                              evaluate_acquisitions)
+from bask.bayesgpr import BayesGPR  # noqa: E402
+from bask.utils import construct_default_kernel, geometric_median, guess_priors  # noqa: E402
+from sklearn.gaussian_process.kernels import (RBF, ConstantKernel, Exponentiation,  # noqa: E402
+                                              Matern, WhiteKernel)
+
+import bench_workloads as W  # noqa: E402
+
+warnings.simplefilter("ignore")
+
+
+def fitted_reference_gp(w, n_desired=None, n_burnin=None, seed=0, kernel=None):
+    gp = BayesGPR(kernel=kernel if kernel is not None else construct_default_kernel(list(range(w.d))),
+                  normalize_y=True, random_state=seed)
+    t0 = time.time()
+    gp.fit(w.X, w.y, noise_vector=w.noise_vector,
+           n_desired_samples=w.n_desired_samples if n_desired is None else n_desired,
+           n_burnin=w.n_burnin if n_burnin is None else n_burnin,
+           n_walkers_per_thread=w.n_walkers, progress=False)
+    print(f"  reference fit: {time.time() - t0:.1f}s, chain {gp.chain_.shape}")
+    return gp
+
+
+def per_theta_vectors(gp, thetas, Xc, n_acq_theta, mes_seed):
+    priors = guess_priors(gp.kernel_)
+    out = {}
+    out["lml"] = np.array([gp.log_marginal_likelihood(t) for t in thetas])
+    out["logprob"] = np.array([gp._log_prob_fn(t, priors=priors, warp_priors=None) for t in thetas])
+    theta_backup = gp.theta
+    mus, stds, alphas, eis, tteis, lcbs, means, mess, qs = ([] for _ in range(9))
+    np.random.seed(mes_seed)
+    uniforms = []
+    for t in thetas[:n_acq_theta]:
+        gp.theta = t
+        alphas.append(gp.alpha_.copy())
+        with gp.noise_set_to_zero():
+            mu, std = gp.predict(Xc, return_std=True)
+        mus.append(mu)
+        stds.append(std)
+        eis.append(ExpectedImprovement()(mu, std))
+        tteis.append(TopTwoEI()(mu, std))
+        lcbs.append(LCB()(mu, std))
+        means.append(Expectation()(mu, std))
+        state = np.random.get_state()
+        uniforms.append(np.random.rand(1000).astype(np.float32))
+        np.random.set_state(state)
+        with np.errstate(all="ignore"):
+            mess.append(MaxValueSearch()(mu, std))
+    # predictive std WITH the noise kernel on, first theta
+    gp.theta = thetas[0]
+    mu_n, std_n = gp.predict(Xc, return_std=True)
+    gp.theta = theta_backup
+    out.update(alpha_=np.array(alphas), mu=np.array(mus), std=np.array(stds), ei=np.array(eis),
+               ttei=np.array(tteis), lcb=np.array(lcbs), mean=np.array(means),
+               mes=np.array(mess), mes_uniforms=np.array(uniforms),
+               mu_noisy=mu_n, std_noisy=std_n)
+    return out
+
+
+def common(gp, w):
+    return dict(X=w.X, y_raw=w.y, noise_vector=w.noise_vector, y_train=gp.y_train_,
+                y_mean=np.atleast_1d(gp.y_train_mean_), y_std=np.atleast_1d(gp.y_train_std_),
+                alpha_vec=np.asarray(gp.alpha, dtype=np.float64) * np.ones(w.n),
+                chain=gp.chain_, pos=np.asarray(gp.pos_), theta_median=gp.theta,
+                lml_at_median=np.atleast_1d(gp.log_marginal_likelihood_value_),
+                noise_=np.atleast_1d(gp.noise_))
+
+
+def sweep_vectors(gp, Xc, acqs, names, n_samples, seed, mes_seed, **kw):
+    np.random.seed(mes_seed)
+    vals = evaluate_acquisitions(Xc, gp, acqs, n_samples=n_samples, random_state=seed, **kw)
+    return {f"sweep_{n}": v for n, v in zip(names, vals)}
+
+
+def g1():
+    print("G1: config 1 (Branin n=20, m=500)")
+    w = W.config1()
+    gp = fitted_reference_gp(w)
+    d = common(gp, w)
+    d["thetas"] = gp.chain_[:16].copy()
+    d["Xc"] = w.candidates
+    d.update(per_theta_vectors(gp, d["thetas"], w.candidates, 16, w.mes_seed))
+    gp.theta = d["theta_median"]
+    d["L_median"], d["K_inv_median"], d["alpha_median"] = gp.L_.copy(), gp.K_inv_.copy(), gp.alpha_.copy()
+    d.update(sweep_vectors(gp, w.candidates,
+                           [ExpectedImprovement(), TopTwoEI(), LCB(), Expectation(), MaxValueSearch()],
+                           ["ei", "ttei", "lcb", "mean", "mes"], 10, 1, w.mes_seed))
+    # full-GP acquisitions at the median theta, noise ON (bask/acquisition.py:106-111)
+    d["vr"] = VarianceReduction()(w.candidates[:200], gp)
+    rs = np.random.RandomState(5)
+    ts = gp.sample_y(w.candidates, sample_mean=True, n_samples=10, random_state=rs)
+    d["pvrs_thompson_idx"] = np.argmin(ts, axis=0).astype(np.int64)
+    d["pvrs"] = PVRS()(w.candidates, gp, n_thompson=10, random_state=np.random.RandomState(5))
+    # joint posterior of a small candidate block at the median theta (noise-free kernel)
+    with gp.noise_set_to_zero():
+        mu_c, cov_c = gp.predict(w.candidates[:48], return_cov=True)
+    d["post_mean48"], d["post_cov48"] = mu_c, cov_c
+    np.savez_compressed(os.path.join(HERE, "g1_branin_n20.npz"), **d)
+
+
+def g2():
+    print("G2: config 2 (Hartmann-6 n=100, m=1000)")
+    w = W.config2()
+    gp = fitted_reference_gp(w)
+    d = common(gp, w)
+    d["thetas"] = gp.chain_[:16].copy()
+    d["Xc"] = w.candidates
+    d.update(per_theta_vectors(gp, d["thetas"], w.candidates, 8, w.mes_seed))
+    gp.theta = d["theta_median"]
+    rs = np.random.RandomState(7)
+    ts = gp.sample_y(w.candidates, sample_mean=True, n_samples=10, random_state=rs)
+    d["pvrs_thompson_idx"] = np.argmin(ts, axis=0).astype(np.int64)
+    t0 = time.time()
+    d["pvrs"] = PVRS()(w.candidates, gp, n_thompson=10, random_state=np.random.RandomState(7))
+    print(f"  reference PVRS over {len(w.candidates)} candidates: {time.time() - t0:.1f}s")
+    d["vr"] = VarianceReduction()(w.candidates[:100], gp)
+    np.savez_compressed(os.path.join(HERE, "g2_hartmann6_n100.npz"), **d)
+
+
+def g3():
+    print("G3: config 3 data (n=500, d=6), candidates cut to 1500, 4 theta")
+    w = W.config3(m=1500)
+    gp = fitted_reference_gp(w, n_desired=128, n_burnin=1)
+    d = common(gp, w)
+    d["thetas"] = gp.chain_[:16].copy()
+    d["Xc"] = w.candidates
+    d.update(per_theta_vectors(gp, d["thetas"], w.candidates, 4, w.mes_seed))
+    gp.theta = d["theta_median"]
+    d.update(sweep_vectors(gp, w.candidates, [MaxValueSearch(), ExpectedImprovement()],
+                           ["mes", "ei"], 3, 1, w.mes_seed))
+    d["alpha_median"] = gp.alpha_.copy()
+    d["L_median_diag"] = np.diag(gp.L_).copy()
+    np.savez_compressed(os.path.join(HERE, "g3_wavy6_n500.npz"), **d)
+
+
+def g4():
+    """Kernel zoo: every kernel form the compiled kernel program must reproduce."""
+    print("G4: kernel zoo (n=40, d=3)")
+    r = np.random.RandomState(123)
+    X = r.uniform(size=(40, 3))
+    y = np.sin(4 * X[:, 0]) + X[:, 1] ** 2 - 0.5 * X[:, 2] + 0.05 * r.randn(40)
+    Xc = r.uniform(size=(64, 3))
+    zoo = {
+        "const_plus_matern15_iso": ConstantKernel(1.0) + Matern(0.4, nu=1.5),
+        "const_times_rbf_ard": ConstantKernel(1.5) * RBF([0.3, 0.5, 0.7]),
+        "matern05_ard_fixedconst": ConstantKernel(2.0, "fixed") * Matern([0.5, 0.4, 0.3], nu=0.5),
+        "exp2_of_sum": Exponentiation(ConstantKernel(0.5) * Matern(0.6, nu=2.5) + RBF([1.0, 1.0, 1.0]), 2.0),
+        "matern_inf_iso": ConstantKernel(1.0) * Matern(0.5, nu=np.inf),
+        "product_of_stationary": ConstantKernel(1.0) * RBF(0.8) * Matern([0.9, 0.8, 0.7], nu=2.5),
+    }
+    d = dict(X=X, y_raw=y, Xc=Xc)
+    for name, kern in zoo.items():
+        gp = BayesGPR(kernel=kern, normalize_y=True, random_state=3)
+        gp.fit(X, y, n_desired_samples=2 * max(8, 2 * (len(kern.theta) + 1)), n_burnin=0,
+               n_walkers_per_thread=max(8, 2 * (len(kern.theta) + 1)), progress=False)
+        thetas = gp.chain_[:6].copy()
+        priors = guess_priors(gp.kernel_)
+        d[f"{name}__thetas"] = thetas
+        d[f"{name}__lml"] = np.array([gp.log_marginal_likelihood(t) for t in thetas])
+        d[f"{name}__logprob"] = np.array([gp._log_prob_fn(t, priors=priors, warp_priors=None) for t in thetas])
+        mus, stds = [], []
+        for t in thetas[:3]:
+            gp.theta = t
+            with gp.noise_set_to_zero():
+                mu, std = gp.predict(Xc, return_std=True)
+            mus.append(mu)
+            stds.append(std)
+        d[f"{name}__mu"], d[f"{name}__std"] = np.array(mus), np.array(stds)
+        d[f"{name}__y_train"] = gp.y_train_
+        d[f"{name}__y_mean"] = np.atleast_1d(gp.y_train_mean_)
+        d[f"{name}__y_std"] = np.atleast_1d(gp.y_train_std_)
+    d["geomedian_in"] = r.randn(50, 4)
+    d["geomedian_out"] = geometric_median(d["geomedian_in"])
+    np.savez_compressed(os.path.join(HERE, "g4_kernel_zoo.npz"), **d)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["g1", "g2", "g3", "g4"]
+    for name in which:
+        globals()[name]()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
