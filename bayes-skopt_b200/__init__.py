@@ -1,0 +1,8 @@
+"""bask_b200 -- B200-native (sm_100a) implementation of bayes-skopt's fully Bayesian GP hot
+path behind the reference's own Python surface (bask/__init__.py:12-35).
+
+Host code is Python/PyTorch (device memory, streams); every numeric step of the path runs in
+hand-written CUDA behind the C ABI of ``libbgp.so`` (include/bgp.h).  No CPU fallback."""
+__version__ = "0.1.0"
+
+from . import _lib  # noqa: F401

@@ -1,0 +1,275 @@
+"""Thin host layer over libbgp: one handle + one CUDA stream per estimator.
+
+PyTorch is used for device memory, the stream and events only; every numeric step on the
+path is a libbgp kernel.  Nothing here falls back to the CPU."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Op, Prior, check
+
+_F64 = torch.float64
+
+
+def _ptr(t):
+    return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
+
+
+def find_zeroable_white(kernel):
+    """The WhiteKernel noise_set_to_zero() switches off: first White that is a direct child of
+    a (nested) Sum, k1 before k2 -- skopt's ``_param_for_white_kernel_in_Sum`` as used by
+    bask/bayesgpr.py:328-333.  Returns (object, "k1__k2"-style parameter name) or (None, None)."""
+    def walk(k, prefix):
+        if type(k).__name__ == "Sum":
+            for name in ("k1", "k2"):
+                child = getattr(k, name)
+                if type(child).__name__ == "WhiteKernel":
+                    return child, prefix + name
+                found = walk(child, prefix + name + "__")
+                if found[0] is not None:
+                    return found
+        return None, None
+    return walk(kernel, "")
+
+
+def compile_kernel(kernel):
+    """Walks a scikit-learn style kernel tree (duck-typed: class names and attributes of
+    sklearn.gaussian_process.kernels, which skopt's kernels subclass) into libbgp's postfix
+    program.  theta slots follow scikit-learn's ordering (k1.theta ++ k2.theta, fixed
+    hyper-parameters take no slot; sklearn:kernels.py:738-766)."""
+    ops, fixed_ls = [], []
+    state = {"theta": 0}
+    white_obj, _ = find_zeroable_white(kernel)
+
+    def fixed(bounds):
+        return isinstance(bounds, str) and bounds == "fixed"
+
+    def walk(k):
+        name = type(k).__name__
+        if name in ("Sum", "Product"):
+            walk(k.k1)
+            walk(k.k2)
+            ops.append(Op(_lib.OP_ADD if name == "Sum" else _lib.OP_MUL, -1, 0, 0, 0.0, 0, 0))
+        elif name == "Exponentiation":
+            walk(k.kernel)
+            ops.append(Op(_lib.OP_POW, -1, 0, 0, float(k.exponent), 0, 0))
+        elif name == "ConstantKernel":
+            if fixed(k.constant_value_bounds):
+                ops.append(Op(_lib.OP_CONST, -1, 0, 0, float(k.constant_value), 0, 0))
+            else:
+                ops.append(Op(_lib.OP_CONST, state["theta"], 0, 0, float(k.constant_value), 0, 0))
+                state["theta"] += 1
+        elif name == "WhiteKernel":
+            flags = _lib.FLAG_ZEROABLE_WHITE if k is white_obj else 0
+            if fixed(k.noise_level_bounds):
+                ops.append(Op(_lib.OP_WHITE, -1, 0, flags, float(k.noise_level), 0, 0))
+            else:
+                ops.append(Op(_lib.OP_WHITE, state["theta"], 0, flags, float(k.noise_level), 0, 0))
+                state["theta"] += 1
+        elif name in ("RBF", "Matern"):
+            if name == "RBF":
+                code = _lib.OP_RBF
+            else:
+                nu = float(k.nu)
+                code = {0.5: _lib.OP_MATERN12, 1.5: _lib.OP_MATERN32, 2.5: _lib.OP_MATERN52,
+                        float("inf"): _lib.OP_RBF}.get(nu)
+                if code is None:
+                    raise NotImplementedError(
+                        f"Matern(nu={nu}) needs the modified Bessel function; libbgp implements "
+                        "nu in {0.5, 1.5, 2.5, inf}")
+            ls = np.atleast_1d(np.asarray(k.length_scale, dtype=np.float64))
+            n_ls = len(ls)
+            if fixed(k.length_scale_bounds):
+                off = len(fixed_ls)
+                if n_ls > 1:
+                    fixed_ls.extend(ls.tolist())
+                ops.append(Op(code, -1, n_ls, 0, float(ls[0]), off, 0))
+            else:
+                ops.append(Op(code, state["theta"], n_ls, 0, float(ls[0]), 0, 0))
+                state["theta"] += n_ls
+        else:
+            raise NotImplementedError(f"kernel {name} is not supported by the B200 path")
+
+    walk(kernel)
+    if len(ops) > _lib.BGP_MAX_OPS:
+        raise NotImplementedError("kernel tree too large for the device program")
+    return ops, fixed_ls, state["theta"]
+
+
+class Factor:
+    """Device-resident factorisation(s): the tiled L / L^-1 slabs, z = L^-1 y, LML, info."""
+
+    def __init__(self, thetas, slabs, z, lml, info):
+        self.thetas, self.slabs, self.z, self.lml, self.info = thetas, slabs, z, lml, info
+
+    def __len__(self):
+        return self.thetas.shape[0]
+
+
+class Engine:
+    def __init__(self, device=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.BgpError("no CUDA device visible: the B200 path has no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        h = C.c_void_p()
+        check(self.lib.bgp_create(C.byref(h), self.device.index), "bgp_create")
+        self.h = h
+        self.n = self.d = self.p = 0
+        self.launches = 0   # kernels enqueued by this engine (bench.py's gpu_launches)
+        self._keep = []
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.bgp_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def _st(self):
+        return C.c_void_p(self.stream.cuda_stream)
+
+    def to_dev(self, a, dtype=_F64):
+        t = torch.as_tensor(np.ascontiguousarray(a))
+        if t.dtype != dtype:
+            t = t.to(dtype)
+        with torch.cuda.stream(self.stream):
+            return t.pin_memory().to(self.device, non_blocking=True)
+
+    def empty(self, *shape, dtype=_F64):
+        with torch.cuda.stream(self.stream):
+            return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def to_host(self, t):
+        self.stream.synchronize()
+        return t.cpu().numpy()
+
+    def sync(self):
+        self.stream.synchronize()
+
+    # ------------------------------------------------------------------ model set-up
+    def set_kernel(self, kernel):
+        ops, fixed_ls, p = compile_kernel(kernel)
+        arr = (Op * len(ops))(*ops)
+        fl = (C.c_double * max(1, len(fixed_ls)))(*fixed_ls)
+        check(self.lib.bgp_set_kernel(self.h, arr, len(ops), p, fl, len(fixed_ls)), "bgp_set_kernel")
+        self.p = p
+
+    def set_priors(self, table):
+        if table is None:
+            check(self.lib.bgp_set_priors(self.h, None, 0), "bgp_set_priors")
+            return
+        arr = (Prior * len(table))()
+        for i, (kind, params) in enumerate(table):
+            arr[i].kind = kind
+            for j, v in enumerate(params):
+                arr[i].p[j] = v
+        check(self.lib.bgp_set_priors(self.h, arr, len(table)), "bgp_set_priors")
+
+    def set_data(self, X, y, alpha):
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        n, d = X.shape
+        alpha = np.ascontiguousarray(np.broadcast_to(np.asarray(alpha, dtype=np.float64), (n,)))
+        Xd, yd, ad = self.to_dev(X), self.to_dev(np.asarray(y, dtype=np.float64).reshape(n)), self.to_dev(alpha)
+        check(self.lib.bgp_set_data(self.h, _ptr(Xd), _ptr(yd), _ptr(ad), n, d, self._st), "bgp_set_data")
+        self.stream.synchronize()
+        self.n, self.d = n, d
+
+    # ------------------------------------------------------------------ K1 + K2
+    def logprob_dev(self, thetas_dev, lp_extra_dev=None, want_lml=False):
+        B = thetas_dev.shape[0]
+        lp = self.empty(B)
+        lml = self.empty(B) if want_lml else None
+        info = self.empty(B, dtype=torch.int32)
+        check(self.lib.bgp_logprob_batched(self.h, _ptr(thetas_dev), B, _ptr(lp_extra_dev), _ptr(lp),
+                                           _ptr(lml), _ptr(info), self._st), "bgp_logprob_batched")
+        self.launches += 1
+        return lp, lml, info
+
+    def logprob(self, thetas, lp_extra=None):
+        th = self.to_dev(np.atleast_2d(thetas))
+        ex = None if lp_extra is None else self.to_dev(lp_extra)
+        lp, lml, info = self.logprob_dev(th, ex, want_lml=True)
+        self.stream.synchronize()
+        return lp.cpu().numpy(), lml.cpu().numpy(), info.cpu().numpy()
+
+    def factorize(self, thetas):
+        th = thetas if torch.is_tensor(thetas) else self.to_dev(np.atleast_2d(thetas))
+        S = th.shape[0]
+        slab = int(self.lib.bgp_factor_slab_doubles(self.h))
+        slabs = self.empty(S, slab)
+        z = self.empty(S, self.n)
+        lml = self.empty(S)
+        info = self.empty(S, dtype=torch.int32)
+        check(self.lib.bgp_factorize_batched(self.h, _ptr(th), S, _ptr(slabs), _ptr(z), _ptr(lml),
+                                             _ptr(info), self._st), "bgp_factorize_batched")
+        self.launches += 1
+        return Factor(th, slabs, z, lml, info)
+
+    def extract(self, factor, index, what):
+        n = self.n
+        out = self.empty(n) if what == _lib.EXTRACT_ALPHA else self.empty(n, n)
+        check(self.lib.bgp_factor_extract(self.h, _ptr(factor.slabs[index]), _ptr(factor.z[index]), what,
+                                          _ptr(out), self._st), "bgp_factor_extract")
+        self.launches += 2 if what == _lib.EXTRACT_KINV else 1
+        return out
+
+    # ------------------------------------------------------------------ K4
+    def predict(self, factor, Xc_dev, thetas_dev=None, noise_off=True, y_mean=0.0, y_std=1.0,
+                zextra=None, want_v=False):
+        th = factor.thetas if thetas_dev is None else thetas_dev
+        S, m = th.shape[0], Xc_dev.shape[0]
+        mu, sd = self.empty(S, m), self.empty(S, m)
+        R = 0 if zextra is None else zextra.shape[1]
+        dots = self.empty(S, R, m) if R else None
+        v_ld = 32 * ((self.n + 31) // 32)
+        v = self.empty(S, m, v_ld) if want_v else None
+        check(self.lib.bgp_predict_batched(self.h, _ptr(th), S, _ptr(factor.slabs), _ptr(factor.z),
+                                           _ptr(Xc_dev), m, 1 if noise_off else 0, float(y_mean),
+                                           float(y_std), _ptr(mu), _ptr(sd), _ptr(zextra), R, _ptr(dots),
+                                           _ptr(v), v_ld, self._st), "bgp_predict_batched")
+        self.launches += 1
+        return mu, sd, dots, v
+
+    def acq(self, kind, mu, sd, p0=float("nan"), gumbel32=None, want_fit=False):
+        S, m = mu.shape
+        per_theta = self.empty(S, m)
+        out = self.empty(m)
+        skipped = self.empty(S, dtype=torch.int32)
+        fit = self.empty(S, 5) if want_fit else None
+        K = 0 if gumbel32 is None else gumbel32.shape[1]
+        check(self.lib.bgp_acq_sweep(self.h, kind, _ptr(mu), _ptr(sd), S, m, float(p0), _ptr(gumbel32), K,
+                                     _ptr(per_theta), _ptr(out), _ptr(skipped), _ptr(fit), self._st),
+              "bgp_acq_sweep")
+        self.launches += {_lib.ACQ_EI: 4, _lib.ACQ_TTEI: 6, _lib.ACQ_MEAN: 4, _lib.ACQ_LCB: 4,
+                          _lib.ACQ_MES: 29}[kind]
+        return out, per_theta, skipped, fit
+
+    def argmax(self, v):
+        idx = self.empty(1, dtype=torch.int64)
+        check(self.lib.bgp_argmax(self.h, _ptr(v), v.shape[0], _ptr(idx), self._st), "bgp_argmax")
+        self.launches += 1
+        return idx
+
+    # ------------------------------------------------------------------ K3
+    def mcmc(self, pos, n_steps, seed, a=2.0, buffers=None):
+        """Device-resident run: returns (pos, lp, chain, lp_chain, accepted) tensors."""
+        W, p = pos.shape
+        if buffers is None or buffers["chain"].shape != (n_steps, W, p):
+            buffers = dict(pos=self.empty(W, p), lp=self.empty(W), chain=self.empty(n_steps, W, p),
+                           lpc=self.empty(n_steps, W), acc=self.empty(W, dtype=torch.int32))
+        with torch.cuda.stream(self.stream):
+            buffers["pos"].copy_(pos if torch.is_tensor(pos) else
+                                 torch.as_tensor(np.ascontiguousarray(pos, dtype=np.float64)).pin_memory(),
+                                 non_blocking=True)
+        check(self.lib.bgp_mcmc_run(self.h, _ptr(buffers["pos"]), _ptr(buffers["lp"]), W, n_steps, float(a),
+                                    C.c_uint64(int(seed) & (2 ** 64 - 1)), _ptr(buffers["chain"]),
+                                    _ptr(buffers["lpc"]), _ptr(buffers["acc"]), self._st), "bgp_mcmc_run")
+        self.launches += 2 + 7 * n_steps
+        return buffers

@@ -1,0 +1,382 @@
+// Acquisition epilogues on the (theta-sample x candidate) predictive moments and the
+// finite-guarded mean over theta samples.  Replaces bask/acquisition.py:112-141 (loop +
+// `if np.all(np.isfinite(tmp_out)): acq_output[j] += tmp_out / n_samples`) and the
+// UncertaintyAcquisition classes: ExpectedImprovement (:154-172), TopTwoEI (:175-194),
+// Expectation (:197-201), LCB (:204-216), MaxValueSearch (:219-267).
+#include "bgp_common.cuh"
+#include "bgp_internal.h"
+
+namespace bgp {
+
+constexpr int MES_PTS = 192;      // trial points evaluated per refinement round (3 x 64)
+constexpr int MES_CH = 2048;      // candidates per block in the quantile search
+constexpr int MES_NEWTON = 10;
+constexpr int ST = 8;             // doubles of per-theta statistics
+constexpr int MS = 16;            // doubles of per-theta MES search state
+
+__device__ __forceinline__ double norm_pdf(double x) { return 0.3989422804014327 * exp(-0.5 * x * x); }
+__device__ __forceinline__ double norm_cdf(double x) {
+  return x > 0.0 ? 1.0 - 0.5 * erfc(x * 0.7071067811865476) : 0.5 * erfc(-x * 0.7071067811865476);
+}
+__device__ __forceinline__ double log_ndtr(double x) {
+  if (x > 0.0) return log1p(-0.5 * erfc(x * 0.7071067811865476));
+  const double t = -x * 0.7071067811865476;
+  if (t < 1.0) return log(0.5 * erfc(t));
+  return log(0.5 * erfcx(t)) - t * t;
+}
+// phi(x)/Phi(x), stable in the lower tail
+__device__ __forceinline__ double hazard_lower(double x) {
+  if (x > 0.0) return norm_pdf(x) / (1.0 - 0.5 * erfc(x * 0.7071067811865476));
+  return 0.7978845608028654 / erfcx(-x * 0.7071067811865476);
+}
+__device__ __forceinline__ double ei_f(double x) { return x * norm_cdf(x) + norm_pdf(x); }
+
+__device__ __forceinline__ bool better_max(double v, long long i, double bv, long long bi) {
+  // numpy argmax: NaN wins, first occurrence wins ties
+  const bool vn = isnan(v), bn = isnan(bv);
+  if (vn != bn) return vn;
+  if (vn) return i < bi;
+  return v > bv || (v == bv && i < bi);
+}
+
+__device__ void block_argmax(double& v, long long& i, double* sv, long long* si) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double ov = __shfl_xor_sync(0xffffffffu, v, o);
+    long long oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (better_max(ov, oi, v, i)) { v = ov; i = oi; }
+  }
+  if (lane == 0) { sv[warp] = v; si[warp] = i; }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    v = lane < nw ? sv[lane] : -INFINITY;
+    i = lane < nw ? si[lane] : (1LL << 62);
+    if (lane >= nw) v = -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      double ov = __shfl_xor_sync(0xffffffffu, v, o);
+      long long oi = __shfl_xor_sync(0xffffffffu, i, o);
+      if (better_max(ov, oi, v, i)) { v = ov; i = oi; }
+    }
+  }
+}
+
+// stats[s] = {min mu, left, right, all-finite(mu,sd)}  (left/right: bask/acquisition.py:239-241)
+__global__ void acq_stats_kernel(const double* __restrict__ mu, const double* __restrict__ sd, int m,
+                                 double* __restrict__ stats, double* __restrict__ pts) {
+  const int s = blockIdx.x;
+  double mn = INFINITY, lf = INFINITY, rt = -INFINITY;
+  int fin = 1;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    const double a = mu[(size_t)s * m + i], b = sd[(size_t)s * m + i];
+    mn = fmin(mn, a); lf = fmin(lf, -a - 3.0 * b); rt = fmax(rt, -a + 5.0 * b);
+    fin &= (isfinite(a) && isfinite(b));
+  }
+  __shared__ double r0[32], r1[32], r2[32];
+  __shared__ int r3[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    lf = fmin(lf, __shfl_xor_sync(0xffffffffu, lf, o));
+    rt = fmax(rt, __shfl_xor_sync(0xffffffffu, rt, o));
+    fin &= __shfl_xor_sync(0xffffffffu, fin, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { r0[warp] = mn; r1[warp] = lf; r2[warp] = rt; r3[warp] = fin; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+      mn = fmin(mn, r0[w]); lf = fmin(lf, r1[w]); rt = fmax(rt, r2[w]); fin &= r3[w];
+    }
+    stats[s * ST + 0] = mn; stats[s * ST + 1] = lf; stats[s * ST + 2] = rt; stats[s * ST + 3] = fin;
+    r0[0] = lf; r1[0] = rt;
+  }
+  __syncthreads();
+  if (pts) {
+    const double l = r0[0], h = r1[0];
+    for (int p = threadIdx.x; p < 64; p += blockDim.x)
+      pts[s * MES_PTS + p] = p == 63 ? h : l + (h - l) * (p / 63.0);
+  }
+}
+
+__global__ void ei_kernel(const double* __restrict__ mu, const double* __restrict__ sd, int m,
+                          const double* __restrict__ stats, double y_opt_in, double* __restrict__ out) {
+  const int s = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const double y_opt = isnan(y_opt_in) ? stats[s * ST + 0] : y_opt_in;
+  const double a = mu[(size_t)s * m + i], b = sd[(size_t)s * m + i];
+  out[(size_t)s * m + i] = (b > 0.0) ? ei_f((y_opt - a) / b) * b : 0.0;
+}
+
+__global__ void argmax_rows_kernel(const double* __restrict__ v, int m, long long* __restrict__ idx) {
+  const int s = blockIdx.x;
+  double bv = -INFINITY;
+  long long bi = 1LL << 62;
+  for (long long i = threadIdx.x; i < m; i += blockDim.x) {
+    const double x = v[(size_t)s * m + i];
+    if (better_max(x, i, bv, bi)) { bv = x; bi = i; }
+  }
+  __shared__ double sv[32];
+  __shared__ long long si[32];
+  block_argmax(bv, bi, sv, si);
+  if (threadIdx.x == 0) idx[s] = bi;
+}
+
+__global__ void ttei_kernel(const double* __restrict__ mu, const double* __restrict__ sd, int m,
+                            const long long* __restrict__ imax, double* __restrict__ out) {
+  const int s = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const long long j = imax[s];
+  const double a = mu[(size_t)s * m + i], b = sd[(size_t)s * m + i];
+  const double aj = mu[(size_t)s * m + j], bj = sd[(size_t)s * m + j];
+  double v = 0.0;
+  if (b > 0.0) {
+    const double outer = sqrt(b * b + bj * bj);
+    v = outer * ei_f((aj - a) / outer);
+  }
+  out[(size_t)s * m + i] = v;
+}
+
+__global__ void mean_lcb_kernel(const double* __restrict__ mu, const double* __restrict__ sd, int m,
+                                int kind, double alpha, double* __restrict__ out) {
+  const int s = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const double a = mu[(size_t)s * m + i], b = sd[(size_t)s * m + i];
+  double v;
+  if (kind == BGP_ACQ_MEAN) v = -a;
+  else v = isinf(alpha) ? b : alpha * b - a;
+  out[(size_t)s * m + i] = v;
+}
+
+// g(x) = sum_i log Phi((x + mu_i)/sd_i) (and optionally g') at npts trial points per theta;
+// deterministic two-stage reduction: part[s][blk][p]
+__global__ void mes_eval_kernel(const double* __restrict__ mu, const double* __restrict__ sd, int m,
+                                const double* __restrict__ pts, int npts, int with_grad,
+                                double* __restrict__ gpart, double* __restrict__ dpart) {
+  const int s = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
+  constexpr int PER = MES_CH / 256;
+  double mean[PER], sdv[PER];
+#pragma unroll
+  for (int e = 0; e < PER; ++e) {
+    const int i = blk * MES_CH + e * 256 + threadIdx.x;
+    if (i < m) { mean[e] = -mu[(size_t)s * m + i]; sdv[e] = sd[(size_t)s * m + i]; }
+    else { mean[e] = 0.0; sdv[e] = -1.0; }   // sd < 0 marks padding
+  }
+  __shared__ double rg[8], rd[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int p = 0; p < npts; ++p) {
+    const double x = pts[s * MES_PTS + p];
+    double g = 0.0, dg = 0.0;
+#pragma unroll
+    for (int e = 0; e < PER; ++e) {
+      if (sdv[e] >= 0.0) {
+        const double t = (x - mean[e]) / sdv[e];
+        g += log_ndtr(t);
+        if (with_grad) dg += hazard_lower(t) / sdv[e];
+      }
+    }
+    g = warp_sum(g);
+    if (with_grad) dg = warp_sum(dg);
+    if (lane == 0) { rg[warp] = g; rd[warp] = dg; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0.0, b = 0.0;
+      for (int w = 0; w < 8; ++w) { a += rg[w]; b += rd[w]; }
+      gpart[((size_t)s * nblk + blk) * MES_PTS + p] = a;
+      if (with_grad) dpart[((size_t)s * nblk + blk) * MES_PTS + p] = b;
+    }
+    __syncthreads();
+  }
+}
+
+// phase 1: bracket on the 64-grid -> 3 x 64 refined points; phase 2: bracket again -> 3 midpoints;
+// phase 3: one safeguarded Newton step; phase 4: Gumbel fit (bask/acquisition.py:251-252)
+__global__ void mes_control_kernel(int phase, int nblk, double* __restrict__ pts,
+                                   const double* __restrict__ gpart, const double* __restrict__ dpart,
+                                   double* __restrict__ st, double* __restrict__ fit) {
+  const int s = blockIdx.x, lane = threadIdx.x;
+  __shared__ double g[MES_PTS], dg[4], x0[MES_PTS];
+  const int npts = phase == 1 ? 64 : (phase == 2 ? MES_PTS : 3);
+  for (int p = lane; p < npts; p += 32) {
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < nblk; ++k) {
+      a += gpart[((size_t)s * nblk + k) * MES_PTS + p];
+      if (phase == 3) b += dpart[((size_t)s * nblk + k) * MES_PTS + p];
+    }
+    g[p] = a; x0[p] = pts[s * MES_PTS + p];
+    if (phase == 3) dg[p] = b;
+  }
+  __syncwarp();
+  double* S = st + s * MS;   // lo[0..2], hi[3..5], x[6..8]
+  const double tau[3] = {-1.3862943611198906, -0.6931471805599453, -0.2876820724517809};
+  if (phase == 1 || phase == 2) {
+    if (lane < 3) {
+      const int q = lane, base = phase == 1 ? 0 : 64 * q;
+      int lo = 0;
+      for (int p = 0; p < 64; ++p) if (g[base + p] <= tau[q]) lo = p;   // g is non-decreasing
+      if (lo > 62) lo = 62;
+      const double xl = x0[base + lo], xh = x0[base + lo + 1];
+      S[q] = xl; S[3 + q] = xh;
+      if (phase == 2) { S[6 + q] = 0.5 * (xl + xh); }
+    }
+    __syncwarp();
+    if (phase == 1) {
+      for (int p = lane; p < MES_PTS; p += 32) {
+        const int q = p >> 6, k = p & 63;
+        const double xl = S[q], xh = S[3 + q];
+        pts[s * MES_PTS + p] = k == 63 ? xh : xl + (xh - xl) * (k / 63.0);
+      }
+    } else if (lane < 3) {
+      pts[s * MES_PTS + lane] = S[6 + lane];
+    }
+  } else if (phase == 3) {
+    if (lane < 3) {
+      const int q = lane;
+      double lo = S[q], hi = S[3 + q];
+      const double x = S[6 + q];
+      if (g[q] <= tau[q]) lo = x; else hi = x;
+      double xn = x + (tau[q] - g[q]) / dg[q];
+      if (!(xn >= lo && xn <= hi)) xn = 0.5 * (lo + hi);   // NaN or outside the bracket: bisect
+      S[q] = lo; S[3 + q] = hi; S[6 + q] = xn;
+      pts[s * MES_PTS + q] = xn;
+    }
+  } else {
+    if (lane == 0) {
+      const double q1 = S[6], med = S[7], q2 = S[8];
+      const double beta = (q1 - q2) / (log(log(4.0 / 3.0)) - log(log(4.0)));
+      const double alpha = med + beta * log(log(2.0));
+      S[9] = alpha; S[10] = beta;
+      if (fit) { fit[s * 5 + 0] = alpha; fit[s * 5 + 1] = beta; fit[s * 5 + 2] = q1; fit[s * 5 + 3] = med; fit[s * 5 + 4] = q2; }
+    }
+  }
+}
+
+// mean_k [ gamma phi(gamma) / (2 Phi(gamma)) - log Phi(gamma) ],  gamma = (maxv_k + mu)/sd
+__global__ void mes_epilogue_kernel(const double* __restrict__ mu, const double* __restrict__ sd, int m,
+                                    const float* __restrict__ gumbel, int K, const double* __restrict__ st,
+                                    double* __restrict__ out) {
+  extern __shared__ double maxv[];
+  const int s = blockIdx.y;
+  const double alpha = st[s * MS + 9], beta = st[s * MS + 10];
+  for (int k = threadIdx.x; k < K; k += blockDim.x)
+    maxv[k] = (double)gumbel[(size_t)s * K + k] * beta + alpha;
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const double mean = -mu[(size_t)s * m + i], b = sd[(size_t)s * m + i];
+  double acc = 0.0;
+  for (int k = 0; k < K; ++k) {
+    const double gam = (maxv[k] - mean) / b;
+    double term;
+    if (gam > 0.0) {
+      const double e = 0.5 * erfc(gam * 0.7071067811865476);
+      term = gam * norm_pdf(gam) / (2.0 * (1.0 - e)) - log1p(-e);
+    } else {
+      const double t = -gam * 0.7071067811865476;
+      if (t < 26.0) {
+        const double ex = erfcx(t);   // Phi = 0.5 ex exp(-t^2), phi = exp(-t^2)/sqrt(2 pi)
+        term = gam * 0.3989422804014327 / ex - (log(0.5 * ex) - t * t);
+      } else {
+        // the reference's naive ratio underflows here (cdf -> 0): keep its non-finite result
+        const double cdf = 0.5 * erfc(t), pdf = norm_pdf(gam);
+        term = gam * pdf / (2.0 * cdf) - (log(0.5 * erfcx(t)) - t * t);
+      }
+    }
+    acc += term;
+  }
+  out[(size_t)s * m + i] = acc / K;
+}
+
+__global__ void finite_rows_kernel(const double* __restrict__ v, int m, const double* __restrict__ stats,
+                                   int32_t* __restrict__ skipped) {
+  const int s = blockIdx.x;
+  int fin = 1;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) fin &= isfinite(v[(size_t)s * m + i]) ? 1 : 0;
+  fin = __syncthreads_and(fin);
+  if (threadIdx.x == 0) skipped[s] = fin ? 0 : 1;
+}
+
+__global__ void combine_kernel(const double* __restrict__ v, int S, int m, const int32_t* __restrict__ skipped,
+                               double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  double acc = 0.0;
+  for (int s = 0; s < S; ++s)
+    if (!skipped[s]) acc += v[(size_t)s * m + i] / S;
+  out[i] = acc;
+}
+
+size_t acq_scratch_doubles(int S, int m) {
+  const size_t nblk = (m + MES_CH - 1) / MES_CH;
+  return (size_t)S * (ST + MS + MES_PTS + 8) + 2 * (size_t)S * nblk * MES_PTS + (size_t)S * m + 64;
+}
+
+cudaError_t launch_acq(const AcqArgs& A, cudaStream_t stream) {
+  const int S = A.S, m = A.m;
+  if (S <= 0) return cudaSuccess;
+  const int nblk = (m + MES_CH - 1) / MES_CH;
+  double* stats = A.scratch;
+  double* st = stats + (size_t)S * ST;
+  double* pts = st + (size_t)S * MS;
+  long long* imax = reinterpret_cast<long long*>(pts + (size_t)S * MES_PTS);
+  double* gpart = pts + (size_t)S * MES_PTS + (size_t)S * 8;
+  double* dpart = gpart + (size_t)S * nblk * MES_PTS;
+  double* tmp = dpart + (size_t)S * nblk * MES_PTS;   // S x m
+  dim3 ge((m + 255) / 256, S);
+  acq_stats_kernel<<<S, 1024, 0, stream>>>(A.mu, A.sd, m, stats, A.kind == BGP_ACQ_MES ? pts : nullptr);
+  switch (A.kind) {
+    case BGP_ACQ_EI:
+      ei_kernel<<<ge, 256, 0, stream>>>(A.mu, A.sd, m, stats, A.p0, A.per_theta);
+      break;
+    case BGP_ACQ_TTEI:
+      ei_kernel<<<ge, 256, 0, stream>>>(A.mu, A.sd, m, stats, A.p0, tmp);
+      argmax_rows_kernel<<<S, 1024, 0, stream>>>(tmp, m, imax);
+      ttei_kernel<<<ge, 256, 0, stream>>>(A.mu, A.sd, m, imax, A.per_theta);
+      break;
+    case BGP_ACQ_MEAN:
+    case BGP_ACQ_LCB:
+      mean_lcb_kernel<<<ge, 256, 0, stream>>>(A.mu, A.sd, m, A.kind, A.p0, A.per_theta);
+      break;
+    case BGP_ACQ_MES: {
+      if (!A.u32 || A.K <= 0) return cudaErrorInvalidValue;
+      dim3 gq(nblk, S);
+      mes_eval_kernel<<<gq, 256, 0, stream>>>(A.mu, A.sd, m, pts, 64, 0, gpart, dpart);
+      mes_control_kernel<<<S, 32, 0, stream>>>(1, nblk, pts, gpart, dpart, st, nullptr);
+      mes_eval_kernel<<<gq, 256, 0, stream>>>(A.mu, A.sd, m, pts, MES_PTS, 0, gpart, dpart);
+      mes_control_kernel<<<S, 32, 0, stream>>>(2, nblk, pts, gpart, dpart, st, nullptr);
+      for (int it = 0; it < MES_NEWTON; ++it) {
+        mes_eval_kernel<<<gq, 256, 0, stream>>>(A.mu, A.sd, m, pts, 3, 1, gpart, dpart);
+        mes_control_kernel<<<S, 32, 0, stream>>>(3, nblk, pts, gpart, dpart, st, nullptr);
+      }
+      mes_control_kernel<<<S, 32, 0, stream>>>(4, nblk, pts, gpart, dpart, st, A.mes_fit);
+      dim3 gm((m + 127) / 128, S);
+      mes_epilogue_kernel<<<gm, 128, A.K * sizeof(double), stream>>>(A.mu, A.sd, m, A.u32, A.K, st, A.per_theta);
+    } break;
+    default: return cudaErrorInvalidValue;
+  }
+  finite_rows_kernel<<<S, 1024, 0, stream>>>(A.per_theta, m, stats, A.skipped);
+  combine_kernel<<<(m + 255) / 256, 256, 0, stream>>>(A.per_theta, S, m, A.skipped, A.out);
+  return cudaGetLastError();
+}
+
+__global__ void argmax_final_kernel(const double* __restrict__ v, int m, long long* __restrict__ idx) {
+  double bv = -INFINITY;
+  long long bi = 1LL << 62;
+  for (long long i = threadIdx.x; i < m; i += blockDim.x) {
+    const double x = v[i];
+    if (better_max(x, i, bv, bi)) { bv = x; bi = i; }
+  }
+  __shared__ double sv[32];
+  __shared__ long long si[32];
+  block_argmax(bv, bi, sv, si);
+  if (threadIdx.x == 0) idx[0] = bi;
+}
+
+cudaError_t launch_argmax(const double* v, int m, long long* idx, double*, cudaStream_t stream) {
+  argmax_final_kernel<<<1, 1024, 0, stream>>>(v, m, idx);
+  return cudaGetLastError();
+}
+
+}  // namespace bgp

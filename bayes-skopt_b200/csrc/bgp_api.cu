@@ -1,0 +1,445 @@
+// C ABI of libbgp (include/bgp.h): handle, argument checking, workspace, CUDA-graph cache.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bgp_common.cuh"
+#include "bgp_internal.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char* what, cudaError_t e = cudaSuccess) {
+  g_err = what;
+  if (e != cudaSuccess) { g_err += ": "; g_err += cudaGetErrorString(e); }
+  return -1;
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t ensure(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e == cudaSuccess) bytes = need;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  template <class T> T* as() { return static_cast<T*>(p); }
+};
+
+struct GraphKey {
+  const void *pos, *lp, *chain, *lpc, *acc;
+  int W, T, n, d, p;
+  double a;
+  bool operator==(const GraphKey& o) const { return std::memcmp(this, &o, sizeof(GraphKey)) == 0; }
+};
+
+}  // namespace
+
+struct bgp_handle_s {
+  int device = 0, sms = 0;
+  DevProgram host_prog;
+  bool have_prog = false, have_priors = false, have_data = false;
+  int n = 0, d = 0, n_priors = 0;
+  DevBuf prog, fixed_ls, priors, X, y, alpha;
+  DevBuf slabs_scratch;      // one factor slab per resident CTA (logprob mode)
+  DevBuf acq_scratch, extract_scratch;
+  DevBuf mc_colour, mc_movers, mc_q, mc_factors, mc_newlp, mc_seed;
+  uint64_t* seed_pinned = nullptr;
+  cudaGraphExec_t graph = nullptr;
+  GraphKey key;
+  bool have_graph = false;
+};
+
+#define CHECK_H(h) if (!(h)) return fail("null handle")
+#define CUDA_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return fail(#expr, _e); } while (0)
+
+extern "C" {
+
+const char* bgp_last_error(void) { return g_err.c_str(); }
+int bgp_version(void) { return 100; }
+
+int bgp_create(bgp_handle_t* out, int device) {
+  if (!out) return fail("null out");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) return fail("no CUDA device: libbgp has no CPU fallback", e);
+  if (device < 0 || device >= count) return fail("bad device index");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail("libbgp is built for sm_100a (B200) only");
+  bgp_handle_s* h = new bgp_handle_s();
+  h->device = device;
+  h->sms = prop.multiProcessorCount;
+  std::memset(&h->key, 0, sizeof(h->key));
+  CUDA_TRY(cudaMallocHost((void**)&h->seed_pinned, sizeof(uint64_t)));
+  CUDA_TRY(h->mc_seed.ensure(sizeof(uint64_t)));
+  *out = h;
+  return 0;
+}
+
+int bgp_destroy(bgp_handle_t h) {
+  CHECK_H(h);
+  cudaSetDevice(h->device);
+  if (h->graph) cudaGraphExecDestroy(h->graph);
+  for (DevBuf* b : {&h->prog, &h->fixed_ls, &h->priors, &h->X, &h->y, &h->alpha, &h->slabs_scratch,
+                    &h->acq_scratch, &h->extract_scratch, &h->mc_colour, &h->mc_movers, &h->mc_q,
+                    &h->mc_factors, &h->mc_newlp, &h->mc_seed})
+    b->release();
+  if (h->seed_pinned) cudaFreeHost(h->seed_pinned);
+  delete h;
+  return 0;
+}
+
+int bgp_set_kernel(bgp_handle_t h, const bgp_op_t* ops, int n_ops, int n_theta, const double* fixed_ls,
+                   int n_fixed_ls) {
+  CHECK_H(h);
+  if (!ops || n_ops <= 0 || n_ops > BGP_MAX_OPS) return fail("bad op count");
+  if (n_theta < 0 || n_theta > BGP_MAX_THETA) return fail("bad theta count");
+  CUDA_TRY(cudaSetDevice(h->device));
+  DevProgram& P = h->host_prog;
+  std::memset(&P, 0, sizeof(P));
+  P.n_ops = n_ops; P.n_theta = n_theta;
+  int leaves = 0, depth = 0;
+  for (int i = 0; i < n_ops; ++i) {
+    P.ops[i] = ops[i];
+    const int c = ops[i].code;
+    if (c >= BGP_OP_RBF && c <= BGP_OP_MATERN52) {
+      if (leaves >= BGP_MAX_LEAVES) return fail("too many stationary leaves");
+      P.leaf_of_op[i] = leaves++;
+      ++depth;
+    } else if (c == BGP_OP_CONST || c == BGP_OP_WHITE) {
+      ++depth;
+    } else if (c == BGP_OP_ADD || c == BGP_OP_MUL) {
+      if (depth < 2) return fail("malformed postfix program");
+      --depth;
+    } else if (c == BGP_OP_POW) {
+      if (depth < 1) return fail("malformed postfix program");
+    } else {
+      return fail("unknown opcode");
+    }
+    if (depth > 4) return fail("kernel tree too deep (stack > 4)");
+  }
+  if (depth != 1) return fail("malformed postfix program");
+  P.n_leaves = leaves;
+  P.d = h->d;
+  if (n_fixed_ls > 0) {
+    CUDA_TRY(h->fixed_ls.ensure(sizeof(double) * n_fixed_ls));
+    CUDA_TRY(cudaMemcpy(h->fixed_ls.p, fixed_ls, sizeof(double) * n_fixed_ls, cudaMemcpyHostToDevice));
+  }
+  CUDA_TRY(h->prog.ensure(sizeof(DevProgram)));
+  CUDA_TRY(cudaMemcpy(h->prog.p, &P, sizeof(DevProgram), cudaMemcpyHostToDevice));
+  h->have_prog = true;
+  h->have_graph = false;
+  return 0;
+}
+
+int bgp_set_priors(bgp_handle_t h, const bgp_prior_t* priors, int n_priors) {
+  CHECK_H(h);
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (n_priors <= 0 || !priors) { h->have_priors = false; h->n_priors = 0; h->have_graph = false; return 0; }
+  if (n_priors > BGP_MAX_THETA) return fail("too many priors");
+  CUDA_TRY(h->priors.ensure(sizeof(bgp_prior_t) * n_priors));
+  CUDA_TRY(cudaMemcpy(h->priors.p, priors, sizeof(bgp_prior_t) * n_priors, cudaMemcpyHostToDevice));
+  h->n_priors = n_priors;
+  h->have_priors = true;
+  h->have_graph = false;
+  return 0;
+}
+
+int bgp_set_data(bgp_handle_t h, const double* X_dev, const double* y_dev, const double* alpha_dev, int n,
+                 int d, void* stream) {
+  CHECK_H(h);
+  if (!X_dev || !y_dev || !alpha_dev || n <= 0 || d <= 0 || d > BGP_MAX_DIM) return fail("bad data arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(h->X.ensure(sizeof(double) * n * d));
+  CUDA_TRY(h->y.ensure(sizeof(double) * n));
+  CUDA_TRY(h->alpha.ensure(sizeof(double) * n));
+  CUDA_TRY(cudaMemcpyAsync(h->X.p, X_dev, sizeof(double) * n * d, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(h->y.p, y_dev, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(h->alpha.p, alpha_dev, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+  if (h->n != n || h->d != d) h->have_graph = false;
+  h->n = n; h->d = d;
+  {
+    cudaError_t e = bgp::prepare_chol(n, d);
+    if (e != cudaSuccess) return fail("n/d too large for the shared-memory plan of the factorisation kernel", e);
+  }
+  if (h->have_prog && h->host_prog.d != d) {
+    h->host_prog.d = d;
+    CUDA_TRY(cudaMemcpyAsync(h->prog.p, &h->host_prog, sizeof(DevProgram), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  h->have_data = true;
+  return 0;
+}
+
+static int ready(bgp_handle_t h) {
+  if (!h->have_prog) return fail("bgp_set_kernel has not been called");
+  if (!h->have_data) return fail("bgp_set_data has not been called");
+  if (h->host_prog.d != h->d) return fail("internal: program dimension mismatch");
+  return 0;
+}
+
+static int logprob_impl(bgp_handle_t h, const double* theta_dev, int batch, const double* lp_extra_dev,
+                        double* lp_dev, double* lml_dev, int32_t* info_dev, cudaStream_t st) {
+  const SlabGeom G = SlabGeom::make(h->n, false);
+  const int slots = h->n <= 64 ? 2 * h->sms : h->sms;
+  CUDA_TRY(h->slabs_scratch.ensure(sizeof(double) * (size_t)G.doubles() * slots));
+  bgp::CholArgs A;
+  A.X = h->X.as<double>(); A.y = h->y.as<double>(); A.alpha = h->alpha.as<double>();
+  A.theta = theta_dev; A.lp_extra = lp_extra_dev; A.lp = lp_dev; A.lml = lml_dev; A.info = info_dev;
+  A.slabs = h->slabs_scratch.as<double>(); A.z_out = nullptr;
+  A.prog = h->prog.as<DevProgram>(); A.fixed_ls = h->fixed_ls.as<double>();
+  A.priors = h->have_priors ? h->priors.as<bgp_prior_t>() : nullptr; A.n_priors = h->n_priors;
+  A.n = h->n; A.d = h->d; A.batch = batch; A.aug = 0; A.slab_per_block = 1;
+  A.dense = nullptr; A.ldd = 0; A.jitter = 0.0;
+  CUDA_TRY(bgp::launch_chol(A, batch < slots ? batch : slots, st));
+  return 0;
+}
+
+int bgp_logprob_batched(bgp_handle_t h, const double* theta_dev, int batch, const double* lp_extra_dev,
+                        double* lp_dev, double* lml_dev, int32_t* info_dev, void* stream) {
+  CHECK_H(h);
+  if (ready(h)) return -1;
+  if (!theta_dev || batch <= 0 || !lp_dev) return fail("bad logprob arguments");
+  if (h->have_priors && h->n_priors != h->host_prog.n_theta) return fail("prior count != theta count");
+  CUDA_TRY(cudaSetDevice(h->device));
+  return logprob_impl(h, theta_dev, batch, lp_extra_dev, lp_dev, lml_dev, info_dev, (cudaStream_t)stream);
+}
+
+int64_t bgp_factor_slab_doubles(bgp_handle_t h) {
+  if (!h || !h->have_data) return -1;
+  return SlabGeom::make(h->n, true).doubles();
+}
+
+int bgp_factorize_batched(bgp_handle_t h, const double* theta_dev, int S, double* slabs_dev, double* z_dev,
+                          double* lml_dev, int32_t* info_dev, void* stream) {
+  CHECK_H(h);
+  if (ready(h)) return -1;
+  if (!theta_dev || S <= 0 || !slabs_dev || !z_dev) return fail("bad factorize arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  bgp::CholArgs A;
+  A.X = h->X.as<double>(); A.y = h->y.as<double>(); A.alpha = h->alpha.as<double>();
+  A.theta = theta_dev; A.lp_extra = nullptr; A.lp = nullptr; A.lml = lml_dev; A.info = info_dev;
+  A.slabs = slabs_dev; A.z_out = z_dev;
+  A.prog = h->prog.as<DevProgram>(); A.fixed_ls = h->fixed_ls.as<double>();
+  A.priors = nullptr; A.n_priors = 0;
+  A.n = h->n; A.d = h->d; A.batch = S; A.aug = 1; A.slab_per_block = 0;
+  A.dense = nullptr; A.ldd = 0; A.jitter = 0.0;
+  CUDA_TRY(bgp::launch_chol(A, S, (cudaStream_t)stream));
+  return 0;
+}
+
+int bgp_factor_extract(bgp_handle_t h, const double* slab_dev, const double* z_dev, int what, double* out_dev,
+                       void* stream) {
+  CHECK_H(h);
+  if (ready(h)) return -1;
+  if (!slab_dev || !out_dev) return fail("bad extract arguments");
+  if (what == BGP_EXTRACT_ALPHA && !z_dev) return fail("alpha extraction needs z");
+  CUDA_TRY(cudaSetDevice(h->device));
+  double* scratch = nullptr;
+  if (what == BGP_EXTRACT_KINV) {
+    CUDA_TRY(h->extract_scratch.ensure(sizeof(double) * (size_t)h->n * h->n));
+    scratch = h->extract_scratch.as<double>();
+  }
+  bgp::ExtractArgs A{slab_dev, z_dev, out_dev, h->n, what};
+  CUDA_TRY(bgp::launch_extract(A, scratch, (cudaStream_t)stream));
+  return 0;
+}
+
+int bgp_predict_batched(bgp_handle_t h, const double* theta_dev, int S, const double* slabs_dev,
+                        const double* z_dev, const double* Xc_dev, int m, int noise_off, double y_mean,
+                        double y_std, double* mu_dev, double* sd_dev, const double* zextra_dev, int R,
+                        double* dots_dev, double* v_dev, int64_t v_ld, void* stream) {
+  CHECK_H(h);
+  if (ready(h)) return -1;
+  if (!theta_dev || S <= 0 || !slabs_dev || !z_dev || !Xc_dev || m <= 0 || !mu_dev || !sd_dev)
+    return fail("bad predict arguments");
+  if (R < 0 || (R > 0 && (!zextra_dev || !dots_dev))) return fail("bad extra right-hand sides");
+  if (v_dev && (v_ld < 32 * ((h->n + 31) / 32) || (v_ld & 3))) return fail("bad v_ld");
+  CUDA_TRY(cudaSetDevice(h->device));
+  bgp::SweepArgs A;
+  A.X = h->X.as<double>(); A.theta = theta_dev; A.slabs = slabs_dev; A.z = z_dev; A.Xc = Xc_dev;
+  A.zextra = zextra_dev; A.mu = mu_dev; A.sd = sd_dev; A.dots = dots_dev; A.v_out = v_dev; A.v_ld = v_ld;
+  A.prog = h->prog.as<DevProgram>(); A.fixed_ls = h->fixed_ls.as<double>();
+  A.y_mean = y_mean; A.y_std = y_std; A.n = h->n; A.d = h->d; A.S = S; A.m = m; A.R = R;
+  A.noise_off = noise_off;
+  cudaError_t e = bgp::launch_sweep(A, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail("sweep launch (n too large for the shared-memory resident tile?)", e);
+  return 0;
+}
+
+int bgp_acq_sweep(bgp_handle_t h, int kind, const double* mu_dev, const double* sd_dev, int S, int m, double p0,
+                  const float* g32_dev, int K, double* per_theta_dev, double* out_dev, int32_t* skipped_dev,
+                  double* mes_fit_dev, void* stream) {
+  CHECK_H(h);
+  if (!mu_dev || !sd_dev || S <= 0 || m <= 0 || !per_theta_dev || !out_dev || !skipped_dev)
+    return fail("bad acquisition arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(h->acq_scratch.ensure(sizeof(double) * bgp::acq_scratch_doubles(S, m)));
+  bgp::AcqArgs A{kind, mu_dev, sd_dev, S, m, p0, g32_dev, K, per_theta_dev, out_dev, skipped_dev, mes_fit_dev,
+                 h->acq_scratch.as<double>()};
+  CUDA_TRY(bgp::launch_acq(A, (cudaStream_t)stream));
+  return 0;
+}
+
+int bgp_argmax(bgp_handle_t h, const double* v_dev, int m, int64_t* idx_dev, void* stream) {
+  CHECK_H(h);
+  if (!v_dev || m <= 0 || !idx_dev) return fail("bad argmax arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(bgp::launch_argmax(v_dev, m, reinterpret_cast<long long*>(idx_dev), nullptr, (cudaStream_t)stream));
+  return 0;
+}
+
+int bgp_posterior_cov(bgp_handle_t h, const double* theta_dev, const double* v_dev, const double* Xc_dev, int m,
+                      int64_t v_ld, int noise_off, double y_std, double* cov_dev, int64_t ldc, void* stream) {
+  CHECK_H(h);
+  if (ready(h)) return -1;
+  if (!theta_dev || !v_dev || !Xc_dev || m <= 0 || !cov_dev || ldc < m || (v_ld & 1)) return fail("bad posterior-cov arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  bgp::PostCovArgs A;
+  A.X = h->X.as<double>(); A.theta = theta_dev; A.v = v_dev; A.Xc = Xc_dev; A.cov = cov_dev; A.v_ld = v_ld;
+  A.ldc = ldc; A.prog = h->prog.as<DevProgram>(); A.fixed_ls = h->fixed_ls.as<double>(); A.y_std = y_std;
+  A.n = h->n; A.d = h->d; A.m = m; A.noise_off = noise_off;
+  CUDA_TRY(bgp::launch_postcov(A, (cudaStream_t)stream));
+  return 0;
+}
+
+int64_t bgp_dense_slab_doubles(int m) { return m > 0 ? SlabGeom::make(m, false).doubles() : -1; }
+
+int bgp_dense_cholesky(bgp_handle_t h, const double* a_dev, int m, int64_t lda, double jitter, double* slab_dev,
+                       int32_t* info_dev, void* stream) {
+  CHECK_H(h);
+  if (!a_dev || m <= 0 || lda < m || !slab_dev || !info_dev) return fail("bad dense-cholesky arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(bgp::prepare_chol(m, 1));
+  bgp::CholArgs A;
+  std::memset(&A, 0, sizeof(A));
+  A.slabs = slab_dev; A.info = info_dev; A.n = m; A.d = 1; A.batch = 1; A.aug = 0; A.slab_per_block = 0;
+  A.dense = a_dev; A.ldd = lda; A.jitter = jitter;
+  CUDA_TRY(bgp::launch_chol(A, 1, (cudaStream_t)stream));
+  if (h->have_data) CUDA_TRY(bgp::prepare_chol(h->n, h->d));
+  return 0;
+}
+
+int bgp_slab_trmm(bgp_handle_t h, const double* slab_dev, int m, const double* e_dev, int ns,
+                  const double* mean_dev, double* out_dev, void* stream) {
+  CHECK_H(h);
+  if (!slab_dev || m <= 0 || !e_dev || ns <= 0 || !out_dev) return fail("bad trmm arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(bgp::launch_slab_trmm(slab_dev, m, e_dev, ns, mean_dev, out_dev, (cudaStream_t)stream));
+  return 0;
+}
+
+int bgp_mcmc_split(bgp_handle_t h, int W, uint64_t seed, int step, int32_t* colour_dev, void* stream) {
+  CHECK_H(h);
+  if (W < 2 || W > 8192 || !colour_dev) return fail("bad split arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(bgp::launch_split(W, seed, nullptr, step, colour_dev, (cudaStream_t)stream));
+  return 0;
+}
+
+int bgp_mcmc_propose(bgp_handle_t h, const double* pos_dev, const int32_t* colour_dev, int W, int half,
+                     double a, uint64_t seed, int step, double* q_dev, double* factors_dev,
+                     int32_t* movers_dev, void* stream) {
+  CHECK_H(h);
+  if (!h->have_prog) return fail("bgp_set_kernel has not been called");
+  if (!pos_dev || !colour_dev || W < 2 || W > 8192 || !q_dev || !factors_dev || !movers_dev)
+    return fail("bad propose arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(bgp::launch_propose(pos_dev, colour_dev, W, h->host_prog.n_theta, half, a, seed, nullptr, step,
+                               q_dev, factors_dev, movers_dev, (cudaStream_t)stream));
+  return 0;
+}
+
+int bgp_mcmc_accept(bgp_handle_t h, double* pos_dev, double* lp_dev, const double* q_dev,
+                    const double* factors_dev, const double* new_lp_dev, const int32_t* movers_dev, int W,
+                    int half, uint64_t seed, int step, int32_t* accepted_dev, double* chain_step_dev,
+                    double* lp_step_dev, void* stream) {
+  CHECK_H(h);
+  if (!h->have_prog) return fail("bgp_set_kernel has not been called");
+  if (!pos_dev || !lp_dev || !q_dev || !factors_dev || !new_lp_dev || !movers_dev) return fail("bad accept arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(bgp::launch_accept(pos_dev, lp_dev, q_dev, factors_dev, new_lp_dev, movers_dev, W,
+                              h->host_prog.n_theta, half, seed, nullptr, step, accepted_dev, chain_step_dev,
+                              lp_step_dev, (cudaStream_t)stream));
+  return 0;
+}
+
+static int mcmc_enqueue(bgp_handle_t h, double* pos, double* lp, int W, int T, double a, double* chain,
+                        double* lpc, int32_t* acc, cudaStream_t st) {
+  const int p = h->host_prog.n_theta;
+  const uint64_t* sp = h->mc_seed.as<uint64_t>();
+  if (acc) CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(int32_t) * W, st));
+  if (logprob_impl(h, pos, W, nullptr, lp, nullptr, nullptr, st)) return -1;
+  for (int t = 0; t < T; ++t) {
+    CUDA_TRY(bgp::launch_split(W, 0, sp, t, h->mc_colour.as<int32_t>(), st));
+    for (int half = 0; half < 2; ++half) {
+      const int ns = half == 0 ? (W + 1) / 2 : W / 2;
+      CUDA_TRY(bgp::launch_propose(pos, h->mc_colour.as<int32_t>(), W, p, half, a, 0, sp, t,
+                                   h->mc_q.as<double>(), h->mc_factors.as<double>(),
+                                   h->mc_movers.as<int32_t>(), st));
+      if (logprob_impl(h, h->mc_q.as<double>(), ns, nullptr, h->mc_newlp.as<double>(), nullptr, nullptr, st))
+        return -1;
+      CUDA_TRY(bgp::launch_accept(pos, lp, h->mc_q.as<double>(), h->mc_factors.as<double>(),
+                                  h->mc_newlp.as<double>(), h->mc_movers.as<int32_t>(), W, p, half, 0, sp, t,
+                                  acc, (half == 1 && chain) ? chain + (size_t)t * W * p : nullptr,
+                                  (half == 1 && lpc) ? lpc + (size_t)t * W : nullptr, st));
+    }
+  }
+  return 0;
+}
+
+int bgp_mcmc_run(bgp_handle_t h, double* pos_dev, double* lp_dev, int W, int T, double a, uint64_t seed,
+                 double* chain_dev, double* lp_chain_dev, int32_t* accepted_dev, void* stream) {
+  CHECK_H(h);
+  if (ready(h)) return -1;
+  const int p = h->host_prog.n_theta;
+  if (!pos_dev || !lp_dev || W < 2 || W > 8192 || T < 0) return fail("bad mcmc arguments");
+  if (W < 2 * p) return fail("fewer walkers than twice the number of dimensions");
+  if (h->have_priors && h->n_priors != p) return fail("prior count != theta count");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(h->mc_colour.ensure(sizeof(int32_t) * W));
+  CUDA_TRY(h->mc_movers.ensure(sizeof(int32_t) * W));
+  CUDA_TRY(h->mc_q.ensure(sizeof(double) * W * p));
+  CUDA_TRY(h->mc_factors.ensure(sizeof(double) * W));
+  CUDA_TRY(h->mc_newlp.ensure(sizeof(double) * W));
+  {  // workspace of the log-posterior kernel must exist before capture starts
+    const SlabGeom G = SlabGeom::make(h->n, false);
+    const int slots = h->n <= 64 ? 2 * h->sms : h->sms;
+    CUDA_TRY(h->slabs_scratch.ensure(sizeof(double) * (size_t)G.doubles() * slots));
+  }
+  *h->seed_pinned = seed;
+  CUDA_TRY(cudaMemcpyAsync(h->mc_seed.p, h->seed_pinned, sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  if (st == nullptr) {  // the legacy default stream cannot be captured: run eagerly
+    return mcmc_enqueue(h, pos_dev, lp_dev, W, T, a, chain_dev, lp_chain_dev, accepted_dev, st);
+  }
+  GraphKey key{pos_dev, lp_dev, chain_dev, lp_chain_dev, accepted_dev, W, T, h->n, h->d, p, a};
+  if (!(h->have_graph && h->key == key)) {
+    if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
+    h->have_graph = false;
+    CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = mcmc_enqueue(h, pos_dev, lp_dev, W, T, a, chain_dev, lp_chain_dev, accepted_dev, st);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(st, &g);
+    if (rc) { if (g) cudaGraphDestroy(g); return -1; }
+    if (e != cudaSuccess) return fail("cudaStreamEndCapture", e);
+    e = cudaGraphInstantiate(&h->graph, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail("cudaGraphInstantiate", e);
+    h->key = key;
+    h->have_graph = true;
+  }
+  CUDA_TRY(cudaGraphLaunch(h->graph, st));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,159 @@
+// Shared device-side pieces of libbgp: covariance-program interpreter, DMMA wrapper,
+// Philox-4x32-10, tiled factor-slab layout.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/bgp.h"
+
+#define BGP_NB 32  // panel width (columns factored together)
+
+// ---------------------------------------------------------------------------- layout
+// Factor slab ("panel-major lower"): panel j holds columns [32j, 32j+32) for storage rows
+// [32j, R) as a row-major (R-32j) x 32 block.  Storage rows:
+//   [0, 32P)            training rows (rows >= n are identity padding)
+//   32P                 the y row: after the factorisation it holds z = L^-1 y
+//   [32P+32, 64P+32)    identity rows: after the factorisation they hold L^-T, i.e. the
+//                       block of panel j, read as [i][c], is (L^-1)[32j+c][i]
+struct SlabGeom {
+  int n, P, R, Rz, Ra;
+  __host__ __device__ static SlabGeom make(int n, bool aug) {
+    SlabGeom g;
+    g.n = n;
+    g.P = (n + BGP_NB - 1) / BGP_NB;
+    g.Rz = BGP_NB * g.P;
+    g.Ra = g.Rz + BGP_NB;
+    g.R = aug ? g.Ra + BGP_NB * g.P : g.Ra;
+    return g;
+  }
+  __host__ __device__ long long off(int j) const {
+    return 32LL * ((long long)j * R - 16LL * j * (j - 1));
+  }
+  __host__ __device__ long long doubles() const { return off(P); }
+  // first element of the L^-T block of panel j
+  __host__ __device__ long long aug_base(int j) const { return off(j) + (long long)(Ra - 32 * j) * 32; }
+};
+
+// ------------------------------------------------------------------- covariance program
+struct DevProgram {
+  int n_ops, n_theta, n_leaves, d;
+  bgp_op_t ops[BGP_MAX_OPS];
+  int leaf_of_op[BGP_MAX_OPS];
+};
+
+// per-theta resolved parameters (shared memory)
+struct ThetaParams {
+  double opval[BGP_MAX_OPS];                     // exp(theta) or the fixed value / exponent
+  double inv_ls[BGP_MAX_LEAVES][BGP_MAX_DIM];    // 1 / length scale per stationary leaf
+};
+
+__device__ __forceinline__ void resolve_theta(const DevProgram& P, const double* __restrict__ theta,
+                                              const double* __restrict__ fixed_ls,
+                                              ThetaParams& out, int tid, int nthreads) {
+  for (int o = tid; o < P.n_ops; o += nthreads) {
+    const bgp_op_t& op = P.ops[o];
+    double v = op.value;
+    if ((op.code == BGP_OP_CONST || op.code == BGP_OP_WHITE) && op.theta_idx >= 0)
+      v = exp(theta[op.theta_idx]);
+    out.opval[o] = v;
+  }
+  for (int o = 0; o < P.n_ops; ++o) {
+    const bgp_op_t& op = P.ops[o];
+    if (op.code < BGP_OP_RBF || op.code > BGP_OP_MATERN52) continue;
+    int leaf = P.leaf_of_op[o];
+    for (int k = tid; k < P.d; k += nthreads) {
+      double ls;
+      if (op.theta_idx >= 0)
+        ls = exp(theta[op.theta_idx + (op.n_ls > 1 ? k : 0)]);
+      else
+        ls = (op.n_ls > 1) ? fixed_ls[op.fixed_ls_offset + k] : op.value;
+      out.inv_ls[leaf][k] = 1.0 / ls;
+    }
+  }
+}
+
+// Evaluates the postfix program for one pair of points.  r2[leaf] = squared scaled
+// distance per stationary leaf; same_point selects the White contribution (Gram diagonal
+// or k(x,x)); white_on=false switches the zeroable White leaf off (noise_set_to_zero).
+__device__ __forceinline__ double pick_leaf(const double* r2, int leaf) {
+  double v = r2[0];
+#pragma unroll
+  for (int l = 1; l < BGP_MAX_LEAVES; ++l) v = (leaf == l) ? r2[l] : v;
+  return v;
+}
+
+__device__ __forceinline__ double eval_program(const DevProgram& P, const ThetaParams& T,
+                                               const double* r2, bool same_point, bool white_on) {
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#define BGP_PUSH(v) { s3 = s2; s2 = s1; s1 = s0; s0 = (v); }
+#define BGP_BIN(expr) { double _a = s1, _b = s0; s0 = (expr); s1 = s2; s2 = s3; }
+  for (int o = 0; o < P.n_ops; ++o) {
+    const int code = P.ops[o].code;
+    switch (code) {
+      case BGP_OP_CONST: BGP_PUSH(T.opval[o]); break;
+      case BGP_OP_WHITE: {
+        bool on = same_point && (white_on || !(P.ops[o].flags & BGP_FLAG_ZEROABLE_WHITE));
+        BGP_PUSH(on ? T.opval[o] : 0.0);
+      } break;
+      case BGP_OP_RBF: BGP_PUSH(exp(-0.5 * pick_leaf(r2, P.leaf_of_op[o]))); break;
+      case BGP_OP_MATERN12: BGP_PUSH(exp(-sqrt(pick_leaf(r2, P.leaf_of_op[o])))); break;
+      case BGP_OP_MATERN32: {
+        double t = sqrt(pick_leaf(r2, P.leaf_of_op[o])) * 1.7320508075688772;
+        BGP_PUSH((1.0 + t) * exp(-t));
+      } break;
+      case BGP_OP_MATERN52: {
+        double t = sqrt(pick_leaf(r2, P.leaf_of_op[o])) * 2.23606797749979;
+        BGP_PUSH((1.0 + t + t * t / 3.0) * exp(-t));
+      } break;
+      case BGP_OP_ADD: BGP_BIN(_a + _b); break;
+      case BGP_OP_MUL: BGP_BIN(_a * _b); break;
+      case BGP_OP_POW: s0 = pow(s0, T.opval[o]); break;
+      default: break;
+    }
+  }
+#undef BGP_PUSH
+#undef BGP_BIN
+  return s0;
+}
+
+// ------------------------------------------------------------------------------- DMMA
+// D(8x8) += A(8x4, row) * B(4x8, col).  Lane l holds A[l>>2][l&3], B[l&3][l>>2],
+// D[l>>2][2(l&3)], D[l>>2][2(l&3)+1].  SASS: DMMA.8x8x4 (tcgen05 has no f64 kind).
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+// ------------------------------------------------------------------------------ Philox
+struct Philox4 {
+  uint32_t c[4];
+};
+__device__ __forceinline__ Philox4 philox4x32_10(uint64_t key, uint32_t c0, uint32_t c1, uint32_t c2,
+                                                 uint32_t c3) {
+  uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+  uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = c3;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
+    uint32_t y0 = hi1 ^ x1 ^ k0, y1 = lo1, y2 = hi0 ^ x3 ^ k1, y3 = lo0;
+    x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  Philox4 o; o.c[0] = x0; o.c[1] = x1; o.c[2] = x2; o.c[3] = x3;
+  return o;
+}
+// uniform in (0,1) with 53 random bits (never 0, never 1)
+__device__ __forceinline__ double u01_from(uint32_t hi, uint32_t lo) {
+  uint64_t bits = (((uint64_t)hi << 32) | lo) >> 11;  // 53 bits
+  return ((double)bits + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+// -------------------------------------------------------------------------- reductions
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}

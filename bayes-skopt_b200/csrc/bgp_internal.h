@@ -1,0 +1,106 @@
+// Host-side internals shared by the translation units of libbgp (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/bgp.h"
+
+struct DevProgram;
+
+namespace bgp {
+
+struct CholArgs {
+  const double* X;       // n x d
+  const double* y;       // n
+  const double* alpha;   // n
+  const double* theta;   // batch x p
+  const double* lp_extra;
+  double* lp;
+  double* lml;
+  int32_t* info;
+  double* slabs;         // scratch (slab_per_block=1) or per-theta output slabs
+  double* z_out;         // batch x n or null
+  const DevProgram* prog;
+  const double* fixed_ls;
+  const bgp_prior_t* priors;
+  int n_priors;
+  int n, d, batch, aug, slab_per_block;
+  const double* dense;   // when set: factor this dense SPD matrix (lower part read) instead of a Gram
+  long long ldd;
+  double jitter;
+};
+cudaError_t prepare_chol(int n, int d);
+cudaError_t launch_chol(const CholArgs& A, int grid, cudaStream_t stream);
+size_t chol_smem_bytes(int nw, int n, int d);
+
+struct SweepArgs {
+  const double* X;        // n x d
+  const double* theta;    // S x p
+  const double* slabs;    // S factor slabs (aug)
+  const double* z;        // S x n
+  const double* Xc;       // m x d
+  const double* zextra;   // S x R x n or null
+  double* mu;             // S x m
+  double* sd;             // S x m
+  double* dots;           // S x R x m or null
+  double* v_out;          // S x m x v_ld or null
+  long long v_ld;
+  const DevProgram* prog;
+  const double* fixed_ls;
+  double y_mean, y_std;
+  int n, d, S, m, R, noise_off;
+};
+cudaError_t launch_sweep(const SweepArgs& A, cudaStream_t stream);
+
+struct ExtractArgs {
+  const double* slab;
+  const double* z;
+  double* out;
+  int n, what;
+};
+cudaError_t launch_extract(const ExtractArgs& A, double* scratch, cudaStream_t stream);
+
+struct AcqArgs {
+  int kind;
+  const double* mu;
+  const double* sd;
+  int S, m;
+  double p0;
+  const float* u32;
+  int K;
+  double* per_theta;   // S x m scratch / output
+  double* out;         // m
+  int32_t* skipped;    // S
+  double* mes_fit;     // S x 5 or null
+  double* scratch;     // workspace (see acq_scratch_doubles)
+};
+size_t acq_scratch_doubles(int S, int m);
+cudaError_t launch_acq(const AcqArgs& A, cudaStream_t stream);
+struct PostCovArgs {
+  const double* X;       // unused (kept for symmetry)
+  const double* theta;   // 1 x p
+  const double* v;       // m x v_ld whitened cross-covariances
+  const double* Xc;      // m x d
+  double* cov;           // m x ldc
+  long long v_ld, ldc;
+  const DevProgram* prog;
+  const double* fixed_ls;
+  double y_std;
+  int n, d, m, noise_off;
+};
+cudaError_t launch_postcov(const PostCovArgs& A, cudaStream_t stream);
+cudaError_t launch_slab_trmm(const double* slab, int m, const double* E, int ns, const double* mean,
+                             double* out, cudaStream_t stream);
+cudaError_t launch_argmax(const double* v, int m, long long* idx, double* scratch, cudaStream_t stream);
+
+cudaError_t launch_split(int W, uint64_t seed, const uint64_t* seed_ptr, int step, int32_t* colour,
+                         cudaStream_t stream);
+cudaError_t launch_propose(const double* pos, const int32_t* colour, int W, int p, int half, double a,
+                           uint64_t seed, const uint64_t* seed_ptr, int step, double* q, double* factors,
+                           int32_t* movers, cudaStream_t stream);
+cudaError_t launch_accept(double* pos, double* lp, const double* q, const double* factors,
+                          const double* new_lp, const int32_t* movers, int W, int p, int half,
+                          uint64_t seed, const uint64_t* seed_ptr, int step, int32_t* accepted,
+                          double* chain_step, double* lp_step, cudaStream_t stream);
+
+}  // namespace bgp
