@@ -136,7 +136,10 @@ class Engine:
         return C.c_void_p(self.stream.cuda_stream)
 
     def to_dev(self, a, dtype=_F64):
-        t = torch.as_tensor(np.ascontiguousarray(a))
+        a = np.ascontiguousarray(a)
+        if not a.flags.writeable:
+            a = a.copy()
+        t = torch.as_tensor(a)
         if t.dtype != dtype:
             t = t.to(dtype)
         with torch.cuda.stream(self.stream):

@@ -51,6 +51,8 @@ _SIGNATURES = {
     "bgp_posterior_cov": [_P, _P, _P, _P, C.c_int, C.c_int64, C.c_int, C.c_double, _P, C.c_int64, _P],
     "bgp_dense_cholesky": [_P, _P, C.c_int, C.c_int64, C.c_double, _P, _P, _P],
     "bgp_dense_slab_doubles": [C.c_int],
+    "bgp_pvrs_combine": [_P, _P, _P, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P],
+    "bgp_vr_combine": [_P, _P, C.c_int, C.c_int64, _P, _P, _P, _P, _P],
     "bgp_slab_trmm": [_P, _P, C.c_int, _P, C.c_int, _P, _P, _P],
 }
 EXPORTED = tuple(_SIGNATURES) + ("bgp_last_error",)

@@ -48,6 +48,7 @@ struct bgp_handle_s {
   int n = 0, d = 0, n_priors = 0;
   DevBuf prog, fixed_ls, priors, X, y, alpha;
   DevBuf slabs_scratch;      // one factor slab per resident CTA (logprob mode)
+  DevBuf xt_scratch;         // scaled inputs per resident CTA when they exceed shared memory
   DevBuf acq_scratch, extract_scratch;
   DevBuf mc_colour, mc_movers, mc_q, mc_factors, mc_newlp, mc_seed;
   uint64_t* seed_pinned = nullptr;
@@ -88,7 +89,7 @@ int bgp_destroy(bgp_handle_t h) {
   CHECK_H(h);
   cudaSetDevice(h->device);
   if (h->graph) cudaGraphExecDestroy(h->graph);
-  for (DevBuf* b : {&h->prog, &h->fixed_ls, &h->priors, &h->X, &h->y, &h->alpha, &h->slabs_scratch,
+  for (DevBuf* b : {&h->prog, &h->fixed_ls, &h->priors, &h->X, &h->y, &h->alpha, &h->slabs_scratch, &h->xt_scratch,
                     &h->acq_scratch, &h->extract_scratch, &h->mc_colour, &h->mc_movers, &h->mc_q,
                     &h->mc_factors, &h->mc_newlp, &h->mc_seed})
     b->release();
@@ -137,6 +138,10 @@ int bgp_set_kernel(bgp_handle_t h, const bgp_op_t* ops, int n_ops, int n_theta, 
   CUDA_TRY(cudaMemcpy(h->prog.p, &P, sizeof(DevProgram), cudaMemcpyHostToDevice));
   h->have_prog = true;
   h->have_graph = false;
+  if (h->have_data) {
+    cudaError_t e = bgp::prepare_chol(h->n, h->d, leaves, false);
+    if (e != cudaSuccess) return fail("n/d too large for the shared-memory plan of the factorisation kernel", e);
+  }
   return 0;
 }
 
@@ -168,7 +173,7 @@ int bgp_set_data(bgp_handle_t h, const double* X_dev, const double* y_dev, const
   if (h->n != n || h->d != d) h->have_graph = false;
   h->n = n; h->d = d;
   {
-    cudaError_t e = bgp::prepare_chol(n, d);
+    cudaError_t e = bgp::prepare_chol(n, d, h->have_prog ? h->host_prog.n_leaves : 1, false);
     if (e != cudaSuccess) return fail("n/d too large for the shared-memory plan of the factorisation kernel", e);
   }
   if (h->have_prog && h->host_prog.d != d) {
@@ -200,7 +205,12 @@ static int logprob_impl(bgp_handle_t h, const double* theta_dev, int batch, cons
   A.priors = h->have_priors ? h->priors.as<bgp_prior_t>() : nullptr; A.n_priors = h->n_priors;
   A.n = h->n; A.d = h->d; A.batch = batch; A.aug = 0; A.slab_per_block = 1;
   A.dense = nullptr; A.ldd = 0; A.jitter = 0.0;
-  CUDA_TRY(bgp::launch_chol(A, batch < slots ? batch : slots, st));
+  A.xt_scratch = nullptr; A.xt_stride = 0;
+  if (size_t xt = bgp::chol_xt_scratch_doubles(h->n, h->d, h->host_prog.n_leaves)) {
+    CUDA_TRY(h->xt_scratch.ensure(sizeof(double) * xt * slots));
+    A.xt_scratch = h->xt_scratch.as<double>(); A.xt_stride = (long long)xt;
+  }
+  CUDA_TRY(bgp::launch_chol(A, batch < slots ? batch : slots, h->host_prog.n_leaves, st));
   return 0;
 }
 
@@ -233,7 +243,12 @@ int bgp_factorize_batched(bgp_handle_t h, const double* theta_dev, int S, double
   A.priors = nullptr; A.n_priors = 0;
   A.n = h->n; A.d = h->d; A.batch = S; A.aug = 1; A.slab_per_block = 0;
   A.dense = nullptr; A.ldd = 0; A.jitter = 0.0;
-  CUDA_TRY(bgp::launch_chol(A, S, (cudaStream_t)stream));
+  A.xt_scratch = nullptr; A.xt_stride = 0;
+  if (size_t xt = bgp::chol_xt_scratch_doubles(h->n, h->d, h->host_prog.n_leaves)) {
+    CUDA_TRY(h->xt_scratch.ensure(sizeof(double) * xt * S));
+    A.xt_scratch = h->xt_scratch.as<double>(); A.xt_stride = (long long)xt;
+  }
+  CUDA_TRY(bgp::launch_chol(A, S, h->host_prog.n_leaves, (cudaStream_t)stream));
   return 0;
 }
 
@@ -319,13 +334,13 @@ int bgp_dense_cholesky(bgp_handle_t h, const double* a_dev, int m, int64_t lda, 
   CHECK_H(h);
   if (!a_dev || m <= 0 || lda < m || !slab_dev || !info_dev) return fail("bad dense-cholesky arguments");
   CUDA_TRY(cudaSetDevice(h->device));
-  CUDA_TRY(bgp::prepare_chol(m, 1));
+  CUDA_TRY(bgp::prepare_chol(m, 1, 0, true));
   bgp::CholArgs A;
   std::memset(&A, 0, sizeof(A));
   A.slabs = slab_dev; A.info = info_dev; A.n = m; A.d = 1; A.batch = 1; A.aug = 0; A.slab_per_block = 0;
   A.dense = a_dev; A.ldd = lda; A.jitter = jitter;
-  CUDA_TRY(bgp::launch_chol(A, 1, (cudaStream_t)stream));
-  if (h->have_data) CUDA_TRY(bgp::prepare_chol(h->n, h->d));
+  CUDA_TRY(bgp::launch_chol(A, 1, 0, (cudaStream_t)stream));
+  if (h->have_data) CUDA_TRY(bgp::prepare_chol(h->n, h->d, h->host_prog.n_leaves, false));
   return 0;
 }
 
@@ -335,6 +350,33 @@ int bgp_slab_trmm(bgp_handle_t h, const double* slab_dev, int m, const double* e
   if (!slab_dev || m <= 0 || !e_dev || ns <= 0 || !out_dev) return fail("bad trmm arguments");
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(bgp::launch_slab_trmm(slab_dev, m, e_dev, ns, mean_dev, out_dev, (cudaStream_t)stream));
+  return 0;
+}
+
+int bgp_pvrs_combine(bgp_handle_t h, const double* theta_dev, const double* xt_dev, int R, const double* xc_dev,
+                     int m, const double* dots_dev, const double* vt_dev, const double* s_dev, double* out_dev,
+                     void* stream) {
+  CHECK_H(h);
+  if (ready(h)) return -1;
+  if (!theta_dev || !xt_dev || R <= 0 || !xc_dev || m <= 0 || !dots_dev || !vt_dev || !s_dev || !out_dev)
+    return fail("bad pvrs arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  bgp::CombineArgs A{h->prog.as<DevProgram>(), h->fixed_ls.as<double>(), theta_dev, xt_dev, xc_dev, dots_dev,
+                     vt_dev, s_dev, nullptr, out_dev, 0, R, m, h->n, h->d};
+  CUDA_TRY(bgp::launch_pvrs_combine(A, (cudaStream_t)stream));
+  return 0;
+}
+
+int bgp_vr_combine(bgp_handle_t h, const double* cov_dev, int m, int64_t ldc, const double* xc_dev,
+                   const double* theta_dev, const double* s_dev, double* out_dev, void* stream) {
+  CHECK_H(h);
+  if (ready(h)) return -1;
+  if (!cov_dev || m <= 0 || ldc < m || !theta_dev || !s_dev || !out_dev) return fail("bad vr arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(h->acq_scratch.ensure(sizeof(double) * 64));
+  bgp::CombineArgs A{h->prog.as<DevProgram>(), h->fixed_ls.as<double>(), theta_dev, nullptr, xc_dev, nullptr,
+                     nullptr, s_dev, cov_dev, out_dev, ldc, 0, m, h->n, h->d};
+  CUDA_TRY(bgp::launch_vr_combine(A, h->acq_scratch.as<double>(), (cudaStream_t)stream));
   return 0;
 }
 
@@ -416,6 +458,8 @@ int bgp_mcmc_run(bgp_handle_t h, double* pos_dev, double* lp_dev, int W, int T, 
     const SlabGeom G = SlabGeom::make(h->n, false);
     const int slots = h->n <= 64 ? 2 * h->sms : h->sms;
     CUDA_TRY(h->slabs_scratch.ensure(sizeof(double) * (size_t)G.doubles() * slots));
+    if (size_t xt = bgp::chol_xt_scratch_doubles(h->n, h->d, h->host_prog.n_leaves))
+      CUDA_TRY(h->xt_scratch.ensure(sizeof(double) * xt * slots));
   }
   *h->seed_pinned = seed;
   CUDA_TRY(cudaMemcpyAsync(h->mc_seed.p, h->seed_pinned, sizeof(uint64_t), cudaMemcpyHostToDevice, st));

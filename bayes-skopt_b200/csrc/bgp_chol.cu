@@ -1,9 +1,10 @@
 // K1+K2: batched-theta Gram build + FP64 Cholesky + forward solve + LML + log-prior,
 // one CTA per theta.  Left-looking blocked factorisation, 32-column panels:
-//   * the Gram matrix is never materialised: every panel tile is generated from X in
-//     DMMA accumulator layout right before it is consumed (fused K1);
+//   * the Gram panel is generated from X by the CTA itself right before it is factored
+//     (fused K1) into the L2-resident factor slab -- the n x n matrix never exists in HBM as
+//     an input;
 //   * trailing updates and the panel triangular solve are DMMA.8x8x4 GEMMs whose A operand
-//     streams from the (L2-resident) factor slab, B operand is staged in shared memory;
+//     streams from the slab in 16-byte loads, B operand is staged in shared memory;
 //   * y rides along as one extra row, so z = L^-1 y (and y^T K^-1 y = |z|^2) falls out of the
 //     same panel solves; in factorise mode identity rows ride along too and come out as
 //     L^-T, which the candidate sweep consumes.
@@ -16,7 +17,8 @@ namespace bgp {
 
 constexpr int KCH = 15;        // previous panels staged in shared memory at once
 constexpr int WS = 40;         // row stride of the 32x32 inverse block (== 8 mod 16)
-constexpr int PS = 34;         // row stride of partial / diagonal blocks
+constexpr int PS = 33;         // row stride of the diagonal block (odd: conflict-free columns)
+constexpr int PP = 34;         // row stride of the K-split partial blocks
 
 template <int NW>
 struct CholSmem {
@@ -24,7 +26,7 @@ struct CholSmem {
   ThetaParams tp;
   double Dblk[32 * PS];              // diagonal block being factored
   double Ws[32 * WS];                // its inverse
-  double Part[4][32 * PS];           // K-split partial sums of the diagonal update
+  double Part[4][32 * PP];           // K-split partial sums of the diagonal update
   double red[NW];
   double inv_diag[32];
   int fail;
@@ -57,68 +59,94 @@ __device__ __forceinline__ double log_prior(const bgp_prior_t* pr, int n, const 
   return lp;
 }
 
-// squared scaled distance per stationary leaf between training row `row` (global memory)
-// and panel column `cl` (pre-scaled copy in shared memory), then the program.
-__device__ __forceinline__ double gram_entry(const DevProgram& P, const ThetaParams& T,
-                                             const double* __restrict__ X, const double* Xc_s,
-                                             int d, int row, int cl, bool same) {
-  double r2[BGP_MAX_LEAVES];
-#pragma unroll
-  for (int l = 0; l < BGP_MAX_LEAVES; ++l) {
-    r2[l] = 0.0;
-    if (l < P.n_leaves) {
-      const double* xc = Xc_s + (size_t)(l * 32 + cl) * d;
-      double s = 0.0;
-      for (int k = 0; k < d; ++k) {
-        double t = __ldg(X + (size_t)row * d + k) * T.inv_ls[l][k] - xc[k];
-        s = fma(t, t, s);
-      }
-      r2[l] = same ? 0.0 : s;
+// ---- warp-level Cholesky + inverse of the 32x32 diagonal block in shared memory ----------
+// Compact (rolled) code on purpose: it runs once per panel on one warp, so straight-line
+// unrolled code would be instruction-fetch bound.  Returns 0 or failing local column + 1
+// (LAPACK dpotrf: pivot <= 0 or NaN).
+__device__ __noinline__ int warp_potrf_inv32(double* D, double* Ws, double* inv_diag, int lane,
+                                             double& logdet, int ncols_real) {
+  int fail = 0;
+  for (int j = 0; j < 32; ++j) {
+    double ajj = D[j * PS + j];
+    if (!(ajj > 0.0)) { if (!fail) fail = j + 1; ajj = 1.0; }
+    const double ljj = sqrt(ajj);
+    const double inv = 1.0 / ljj;
+    const double v = D[lane * PS + j];
+    const double lij = lane > j ? v * inv : (lane == j ? ljj : 0.0);
+    __syncwarp();
+    D[lane * PS + j] = lij;
+    if (lane == j) inv_diag[j] = inv;
+    __syncwarp();
+#pragma unroll 4
+    for (int k = j + 1; k < 32; ++k) {
+      const double lkj = D[k * PS + j];
+      if (lane >= k) D[lane * PS + k] = fma(-lij, lkj, D[lane * PS + k]);
     }
+    __syncwarp();
   }
-  return eval_program(P, T, r2, same, true);
+  if (lane < ncols_real) logdet += log(D[lane * PS + lane]);
+  // W = L^-1: lane c solves column c by forward substitution (4 partial sums break the chain)
+  for (int i = 0; i < 32; ++i) {
+    double s0 = (i == lane) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int k = 0;
+    for (; k + 4 <= i; k += 4) {
+      s0 = fma(-D[i * PS + k], Ws[k * WS + lane], s0);
+      s1 = fma(-D[i * PS + k + 1], Ws[(k + 1) * WS + lane], s1);
+      s2 = fma(-D[i * PS + k + 2], Ws[(k + 2) * WS + lane], s2);
+      s3 = fma(-D[i * PS + k + 3], Ws[(k + 3) * WS + lane], s3);
+    }
+    for (; k < i; ++k) s0 = fma(-D[i * PS + k], Ws[k * WS + lane], s0);
+    Ws[i * WS + lane] = (i >= lane) ? ((s0 + s1) + (s2 + s3)) * inv_diag[i] : 0.0;
+  }
+  __syncwarp();
+  return fail;
 }
 
-// ---- warp-level Cholesky + inverse of the 32x32 diagonal block (lane i owns row i) ----
-// Returns 0 or failing local column + 1 (LAPACK dpotrf: pivot <= 0 or NaN).
-__device__ int warp_potrf_inv32(double* Dblk, double* Ws, double* inv_diag, int lane,
-                                double& logdet, int ncols_real) {
-  double a[32];
+// Gram entries of panel k (rows [32k, n) x 32 columns, lower part) -> slab.  Each warp takes
+// four rows at a time, lanes are the 32 columns; scaled coordinates come from the transposed
+// shared-memory copy Xt[leaf][dim][npad] (conflict-free for lanes, broadcast for rows).
+template <int NW>
+__device__ __forceinline__ void gram_panel(const DevProgram& PR, const ThetaParams& TP, const double* Xt,
+                                           int npad, const double* __restrict__ alpha, double* slab,
+                                           const SlabGeom& G, int k, int n, int d, int warp, int lane) {
+  const int c0 = 32 * k, col = c0 + lane;
+  double* base = slab + G.off(k);
+  for (int r0 = c0 + 4 * warp; r0 < n; r0 += 4 * NW) {
+    double r2[4][BGP_MAX_LEAVES];
 #pragma unroll
-  for (int c = 0; c < 32; ++c) a[c] = Dblk[lane * PS + c];
-  int fail = 0;
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    double ajj = __shfl_sync(0xffffffffu, a[j], j);
-    if (!(ajj > 0.0)) { fail = fail ? fail : j + 1; ajj = 1.0; }
-    double ljj = sqrt(ajj);
-    double inv = 1.0 / ljj;
-    if (j < ncols_real) logdet += log(ljj);
-    double lij = (lane == j) ? ljj : a[j] * inv;
-    a[j] = lij;
-    if (lane == 0) inv_diag[j] = inv;
+      for (int l = 0; l < BGP_MAX_LEAVES; ++l) r2[a][l] = 0.0;
 #pragma unroll
-    for (int k = j + 1; k < 32; ++k) {
-      double lkj = __shfl_sync(0xffffffffu, lij, k);
-      a[k] = fma(-lij, lkj, a[k]);   // rows i >= k keep it; others are never read again
+    for (int l = 0; l < BGP_MAX_LEAVES; ++l) {
+      if (l < PR.n_leaves) {
+        const double* xl = Xt + (size_t)l * d * npad;
+        for (int kk = 0; kk < d; ++kk) {
+          const double* xr = xl + (size_t)kk * npad;
+          const double xc = xr[col];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            const double t = xr[min(r0 + a, npad - 1)] - xc;
+            r2[a][l] = fma(t, t, r2[a][l]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int row = r0 + a;
+      if (row < n && col <= row) {
+        const bool same = row == col;
+        if (same) {
+#pragma unroll
+          for (int l = 0; l < BGP_MAX_LEAVES; ++l) r2[a][l] = 0.0;
+        }
+        double v = eval_program(PR, TP, r2[a], same, true);
+        if (same) v += alpha[row];
+        base[(size_t)(row - c0) * 32 + lane] = v;
+      }
     }
   }
-  // L back to shared memory (upper part zero)
-#pragma unroll
-  for (int c = 0; c < 32; ++c) Dblk[lane * PS + c] = (c <= lane) ? a[c] : 0.0;
-  __syncwarp();
-  // inverse: lane c solves column c of W = L^-1 by forward substitution
-  double w[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    double s = (i == lane) ? 1.0 : 0.0;
-#pragma unroll
-    for (int k = 0; k < i; ++k) s = fma(-Dblk[i * PS + k], w[k], s);
-    w[i] = (i >= lane) ? s * inv_diag[i] : 0.0;
-  }
-#pragma unroll
-  for (int i = 0; i < 32; ++i) Ws[i * WS + lane] = w[i];
-  return fail;
 }
 
 template <int NW>
@@ -129,12 +157,14 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
   const int r = lane >> 2, q = lane & 3;
   const int n = A.n, d = A.d;
   const SlabGeom G = SlabGeom::make(n, A.aug != 0);
-  const int P = G.P;
+  const int P = G.P, npad = 32 * P;
   const int kch = P - 1 < KCH ? (P - 1 > 0 ? P - 1 : 1) : KCH;
   const int bstride = 32 * kch + 8;
-  double* Xc_s = reinterpret_cast<double*>(smem_raw + ((sizeof(CholSmem<NW>) + 15) & ~size_t(15)));
-  double* Bs = Xc_s + (size_t)BGP_MAX_LEAVES * 32 * d;  // 32 x bstride
-  // program -> shared (once per CTA)
+  double* Bs = reinterpret_cast<double*>(smem_raw + ((sizeof(CholSmem<NW>) + 15) & ~size_t(15)));  // 32 x bstride
+  // [leaf][dim][npad] scaled training inputs (Gram mode): shared memory when it fits, else a
+  // per-CTA global scratch (same layout, L1/L2 cached)
+  double* Xt = A.xt_scratch ? A.xt_scratch + (size_t)blockIdx.x * A.xt_stride
+                            : Bs + (size_t)32 * bstride;
   if (A.prog) {
     const int* src = reinterpret_cast<const int*>(A.prog);
     int* dst = reinterpret_cast<int*>(&S.prog);
@@ -152,17 +182,17 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
     if (tid == 0) S.fail = 0;
     double logdet = 0.0, zz = 0.0;   // meaningful in warp 0 / z-row owners
     __syncthreads();
+    if (!A.dense) {
+      for (int e = tid; e < PR.n_leaves * d * npad; e += NW * 32) {
+        const int l = e / (d * npad), rem = e - l * d * npad, kk = rem / npad, i = rem - kk * npad;
+        Xt[e] = (i < n) ? A.X[(size_t)i * d + kk] * S.tp.inv_ls[l][kk] : 0.0;
+      }
+      __syncthreads();
+    }
 
     for (int k = 0; k < P; ++k) {
       const int c0 = 32 * k;
-      // scaled copies of the panel's 32 training points, per stationary leaf
-      if (!A.dense) {
-        for (int e = tid; e < PR.n_leaves * 32 * d; e += NW * 32) {
-          int l = e / (32 * d), rem = e - l * 32 * d, cl = rem / d, kk = rem - cl * d;
-          int row = c0 + cl;
-          Xc_s[e] = (row < n) ? A.X[(size_t)row * d + kk] * S.tp.inv_ls[l][kk] : 0.0;
-        }
-      }
+      if (!A.dense) gram_panel<NW>(PR, S.tp, Xt, npad, A.alpha, slab, G, k, n, d, warp, lane);
       // ------------------------------------------------ phase 1: diagonal block
       double acc[4][4][2];
 #pragma unroll
@@ -202,27 +232,21 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
         for (int t = 0; t < 4; ++t)
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            S.Part[warp][(8 * t + r) * PS + 8 * u + 2 * q] = acc[t][u][0];
-            S.Part[warp][(8 * t + r) * PS + 8 * u + 2 * q + 1] = acc[t][u][1];
+            S.Part[warp][(8 * t + r) * PP + 8 * u + 2 * q] = acc[t][u][0];
+            S.Part[warp][(8 * t + r) * PP + 8 * u + 2 * q + 1] = acc[t][u][1];
           }
       }
-      __syncthreads();
+      __syncthreads();   // also makes the Gram panel written above visible to the whole CTA
       for (int e = tid; e < 1024; e += NW * 32) {
-        int rl = e >> 5, cl = e & 31;
+        const int rl = e >> 5, cl = e & 31;
         double v = 0.0;
         if (cl <= rl) {
-          int row = c0 + rl, col = c0 + cl;
+          const int row = c0 + rl, col = c0 + cl;
           if (row < n && col < n) {
-            if (A.dense) {
-              v = A.dense[(size_t)row * A.ldd + col] + (row == col ? A.jitter : 0.0);
-            } else {
-              v = gram_entry(PR, S.tp, A.X, Xc_s, d, row, cl, row == col);
-              if (row == col) v += A.alpha[row];
-            }
-            double s = 0.0;
-            if (k > 0) s = S.Part[0][rl * PS + cl] + S.Part[1][rl * PS + cl] +
-                           S.Part[2][rl * PS + cl] + S.Part[3][rl * PS + cl];
-            v -= s;
+            v = A.dense ? A.dense[(size_t)row * A.ldd + col] + (row == col ? A.jitter : 0.0)
+                        : slab[G.off(k) + (size_t)rl * 32 + cl];
+            if (k > 0) v -= (S.Part[0][rl * PP + cl] + S.Part[1][rl * PP + cl]) +
+                            (S.Part[2][rl * PP + cl] + S.Part[3][rl * PP + cl]);
           } else {
             v = (row == col) ? 1.0 : 0.0;
           }
@@ -233,7 +257,6 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
       if (warp == 0) {
         int f = warp_potrf_inv32(S.Dblk, S.Ws, S.inv_diag, lane, logdet, min(32, n - c0));
         if (f && lane == 0) S.fail = c0 + f;
-        __syncwarp();
         // L_kk -> slab (diag group rows of panel k)
         for (int e = lane; e < 1024; e += 32)
           slab[G.off(k) + e] = S.Dblk[(e >> 5) * PS + (e & 31)];
@@ -321,28 +344,37 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
           }
         }
         if (!valid) continue;
-        // C = init - acc, in accumulator layout
+        // C = init - acc, in accumulator layout (init: Gram panel in the slab / y / identity)
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           if (t >= mt) continue;
           const int row = rb + 8 * t + r;
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int cl = 8 * u + 2 * q + e, col = c0 + cl;
-              double v0 = 0.0;
-              if (kind == 0) {
-                if (row < n && col < n)
-                  v0 = A.dense ? A.dense[(size_t)row * A.ldd + col]
-                               : gram_entry(PR, S.tp, A.X, Xc_s, d, row, cl, false);
-              } else if (kind == 1) {
-                if (row == G.Rz && col < n && A.y) v0 = A.y[col];
-              } else {
-                v0 = (row - G.Ra == col) ? 1.0 : 0.0;
+            const int cl = 8 * u + 2 * q, col = c0 + cl;
+            double2 v0 = make_double2(0.0, 0.0);
+            if (kind == 0) {
+              if (row < n) {
+                if (A.dense) {
+                  if (col < n) v0.x = A.dense[(size_t)row * A.ldd + col];
+                  if (col + 1 < n) v0.y = A.dense[(size_t)row * A.ldd + col + 1];
+                } else {
+                  v0 = *reinterpret_cast<const double2*>(slab + G.off(k) + (size_t)(row - c0) * 32 + cl);
+                  if (col >= n) v0.x = 0.0;
+                  if (col + 1 >= n) v0.y = 0.0;
+                }
               }
-              acc[t][u][e] = v0 - acc[t][u][e];
+            } else if (kind == 1) {
+              if (row == G.Rz && A.y) {
+                if (col < n) v0.x = A.y[col];
+                if (col + 1 < n) v0.y = A.y[col + 1];
+              }
+            } else {
+              v0.x = (row - G.Ra == col) ? 1.0 : 0.0;
+              v0.y = (row - G.Ra == col + 1) ? 1.0 : 0.0;
             }
+            acc[t][u][0] = v0.x - acc[t][u][0];
+            acc[t][u][1] = v0.y - acc[t][u][1];
           }
         }
         // X = C * W^T through DMMA, in place (descending output tile)
@@ -393,6 +425,7 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
 
     // ------------------------------------------------------------------ epilogue
     zz = warp_sum(zz);
+    if (warp == 0) logdet = warp_sum(logdet);
     if (lane == 0) S.red[warp] = zz;
     __syncthreads();
     if (tid == 0) {
@@ -405,7 +438,6 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
         lml = -0.5 * ztz - logdet - 0.5 * n * 1.8378770664093453;
         lp = lml;
         if (A.priors) lp += log_prior(A.priors, A.n_priors, theta);
-        if (A.dense) lp = lml;
         if (A.lp_extra) lp += A.lp_extra[b];
         if (!isfinite(lp)) lp = -INFINITY;
       }
@@ -417,27 +449,42 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
   }
 }
 
-size_t chol_smem_bytes(int nw, int n, int d) {
+static int pick_nw(int n) { return n <= 64 ? 4 : 16; }
+
+static size_t smem_base(int n) {
   const int P = (n + 31) / 32;
   const int kch = P - 1 < KCH ? (P - 1 > 0 ? P - 1 : 1) : KCH;
-  size_t base = nw == 16 ? sizeof(CholSmem<16>) : sizeof(CholSmem<4>);
+  size_t base = pick_nw(n) == 16 ? sizeof(CholSmem<16>) : sizeof(CholSmem<4>);
   base = (base + 15) & ~size_t(15);
-  return base + sizeof(double) * ((size_t)BGP_MAX_LEAVES * 32 * d + (size_t)32 * (32 * kch + 8));
+  return base + sizeof(double) * (size_t)32 * (32 * kch + 8);
+}
+
+// doubles of per-CTA global scratch the scaled inputs need when they do not fit in shared memory
+size_t chol_xt_doubles(int n, int d, int n_leaves) {
+  return (size_t)(n_leaves > 0 ? n_leaves : 1) * d * (32 * ((n + 31) / 32));
+}
+size_t chol_xt_scratch_doubles(int n, int d, int n_leaves) {
+  const size_t xt = chol_xt_doubles(n, d, n_leaves);
+  return smem_base(n) + sizeof(double) * xt <= 226 * 1024 ? 0 : xt;
+}
+
+static size_t chol_smem_bytes(int n, int d, int n_leaves, bool dense) {
+  if (dense || chol_xt_scratch_doubles(n, d, n_leaves)) return smem_base(n);
+  return smem_base(n) + sizeof(double) * chol_xt_doubles(n, d, n_leaves);
 }
 
 // opt-in to the large dynamic shared-memory carve-out (must happen outside stream capture)
-cudaError_t prepare_chol(int n, int d) {
-  const int nw = n <= 64 ? 4 : 16;
-  const size_t smem = chol_smem_bytes(nw, n, d);
+cudaError_t prepare_chol(int n, int d, int n_leaves, bool dense) {
+  const size_t smem = chol_smem_bytes(n, d, n_leaves, dense);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  return nw == 4 ? cudaFuncSetAttribute(chol_lml_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                 : cudaFuncSetAttribute(chol_lml_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  return pick_nw(n) == 4
+             ? cudaFuncSetAttribute(chol_lml_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+             : cudaFuncSetAttribute(chol_lml_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
-cudaError_t launch_chol(const CholArgs& A, int grid, cudaStream_t stream) {
-  const int nw = A.n <= 64 ? 4 : 16;
-  const size_t smem = chol_smem_bytes(nw, A.n, A.d);
-  if (nw == 4) chol_lml_kernel<4><<<grid, 128, smem, stream>>>(A);
+cudaError_t launch_chol(const CholArgs& A, int grid, int n_leaves, cudaStream_t stream) {
+  const size_t smem = chol_smem_bytes(A.n, A.d, n_leaves, A.dense != nullptr);
+  if (pick_nw(A.n) == 4) chol_lml_kernel<4><<<grid, 128, smem, stream>>>(A);
   else chol_lml_kernel<16><<<grid, 512, smem, stream>>>(A);
   return cudaGetLastError();
 }

@@ -28,10 +28,12 @@ struct CholArgs {
   const double* dense;   // when set: factor this dense SPD matrix (lower part read) instead of a Gram
   long long ldd;
   double jitter;
+  double* xt_scratch;    // per-CTA scratch for the scaled inputs when they do not fit in shared memory
+  long long xt_stride;
 };
-cudaError_t prepare_chol(int n, int d);
-cudaError_t launch_chol(const CholArgs& A, int grid, cudaStream_t stream);
-size_t chol_smem_bytes(int nw, int n, int d);
+cudaError_t prepare_chol(int n, int d, int n_leaves, bool dense);
+size_t chol_xt_scratch_doubles(int n, int d, int n_leaves);
+cudaError_t launch_chol(const CholArgs& A, int grid, int n_leaves, cudaStream_t stream);
 
 struct SweepArgs {
   const double* X;        // n x d
@@ -89,6 +91,22 @@ struct PostCovArgs {
   int n, d, m, noise_off;
 };
 cudaError_t launch_postcov(const PostCovArgs& A, cudaStream_t stream);
+struct CombineArgs {
+  const DevProgram* prog;
+  const double* fixed_ls;
+  const double* theta;   // 1 x p
+  const double* Xt;      // R x d Thompson points
+  const double* Xc;      // m x d candidates
+  const double* dots;    // R x m
+  const double* vt;      // R x n
+  const double* s;       // m Schur complements
+  const double* cov;     // m x ldc (VR)
+  double* out;           // m
+  long long ldc;
+  int R, m, n, d;
+};
+cudaError_t launch_pvrs_combine(const CombineArgs& A, cudaStream_t stream);
+cudaError_t launch_vr_combine(const CombineArgs& A, double* scratch, cudaStream_t stream);
 cudaError_t launch_slab_trmm(const double* slab, int m, const double* E, int ns, const double* mean,
                              double* out, cudaStream_t stream);
 cudaError_t launch_argmax(const double* v, int m, long long* idx, double* scratch, cudaStream_t stream);

@@ -131,4 +131,89 @@ cudaError_t launch_slab_trmm(const double* slab, int m, const double* E, int ns,
   return cudaGetLastError();
 }
 
+// PVRS epilogue (Schur form of bask/acquisition.py:328-339):
+//   out[i] = sum_t |v_t|^2 + (k(xt_t, xc_i) - dots[t][i])^2 / s_i
+__global__ void __launch_bounds__(256) pvrs_combine_kernel(CombineArgs A) {
+  __shared__ PostSmem S;
+  __shared__ double base_s;
+  __shared__ double red[8];
+  const int tid = threadIdx.x;
+  {
+    const int* src = reinterpret_cast<const int*>(A.prog);
+    int* dst = reinterpret_cast<int*>(&S.prog);
+    for (int i = tid; i < (int)(sizeof(DevProgram) / 4); i += 256) dst[i] = src[i];
+  }
+  __syncthreads();
+  resolve_theta(S.prog, A.theta, A.fixed_ls, S.tp, tid, 256);
+  double b = 0.0;
+  for (int e = tid; e < A.R * A.n; e += 256) b = fma(A.vt[e], A.vt[e], b);
+  b = warp_sum(b);
+  if ((tid & 31) == 0) red[tid >> 5] = b;
+  __syncthreads();
+  if (tid == 0) { double t = 0.0; for (int w = 0; w < 8; ++w) t += red[w]; base_s = t; }
+  __syncthreads();
+  const int i = blockIdx.x * 256 + tid;
+  if (i >= A.m) return;
+  double acc = base_s;
+  const double si = A.s[i];
+  for (int t = 0; t < A.R; ++t) {
+    double r2[BGP_MAX_LEAVES];
+#pragma unroll
+    for (int l = 0; l < BGP_MAX_LEAVES; ++l) {
+      r2[l] = 0.0;
+      if (l < S.prog.n_leaves) {
+        double a2 = 0.0;
+        for (int kk = 0; kk < A.d; ++kk) {
+          const double tt = A.Xt[(size_t)t * A.d + kk] * S.tp.inv_ls[l][kk] - A.Xc[(size_t)i * A.d + kk] * S.tp.inv_ls[l][kk];
+          a2 = fma(tt, tt, a2);
+        }
+        r2[l] = a2;
+      }
+    }
+    const double c = eval_program(S.prog, S.tp, r2, false, true) - A.dots[(size_t)t * A.m + i];
+    acc += c * c / si;
+  }
+  A.out[i] = acc;
+}
+
+// VR epilogue: out[i] = sum_t (k0 - C[t][t]) + sum_t C[t][i]^2 / s_i   (C: noise-free posterior cov)
+__global__ void __launch_bounds__(256) vr_base_kernel(CombineArgs A, double* base_out) {
+  __shared__ PostSmem S;
+  __shared__ double red[8];
+  const int tid = threadIdx.x;
+  {
+    const int* src = reinterpret_cast<const int*>(A.prog);
+    int* dst = reinterpret_cast<int*>(&S.prog);
+    for (int i = tid; i < (int)(sizeof(DevProgram) / 4); i += 256) dst[i] = src[i];
+  }
+  __syncthreads();
+  resolve_theta(S.prog, A.theta, A.fixed_ls, S.tp, tid, 256);
+  __syncthreads();
+  double r2[BGP_MAX_LEAVES] = {0, 0, 0, 0};
+  const double k0 = eval_program(S.prog, S.tp, r2, true, false);
+  double b = 0.0;
+  for (int t = tid; t < A.m; t += 256) b += k0 - A.cov[(size_t)t * A.ldc + t];
+  b = warp_sum(b);
+  if ((tid & 31) == 0) red[tid >> 5] = b;
+  __syncthreads();
+  if (tid == 0) { double t = 0.0; for (int w = 0; w < 8; ++w) t += red[w]; *base_out = t; }
+}
+__global__ void __launch_bounds__(256) vr_cols_kernel(CombineArgs A, const double* base) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= A.m) return;
+  double acc = 0.0;
+  for (int t = 0; t < A.m; ++t) { const double c = A.cov[(size_t)t * A.ldc + i]; acc = fma(c, c, acc); }
+  A.out[i] = *base + acc / A.s[i];
+}
+
+cudaError_t launch_pvrs_combine(const CombineArgs& A, cudaStream_t stream) {
+  pvrs_combine_kernel<<<(A.m + 255) / 256, 256, 0, stream>>>(A);
+  return cudaGetLastError();
+}
+cudaError_t launch_vr_combine(const CombineArgs& A, double* scratch, cudaStream_t stream) {
+  vr_base_kernel<<<1, 256, 0, stream>>>(A, scratch);
+  vr_cols_kernel<<<(A.m + 255) / 256, 256, 0, stream>>>(A, scratch);
+  return cudaGetLastError();
+}
+
 }  // namespace bgp

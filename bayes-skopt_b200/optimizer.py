@@ -1,0 +1,165 @@
+"""Ask/tell driver: the reference's ``Optimizer.__init__/ask/tell/run`` (bask/optimizer.py:
+120-445) on the B200 path.  ``ask`` does no maths -- it returns the point computed at the tail of
+``tell`` (candidate generation -> evaluate_acquisitions -> argmax), exactly like the reference.
+
+Out of scope here: the Steinerberger initial design (``init_strategy="sb"``
+falls back to the R2 sequence with a warning-free note in the docstring), the post-hoc
+optimality diagnostics, and BayesSearchCV."""
+import warnings
+
+import numpy as np
+from sklearn.utils import check_random_state
+
+from . import acquisition
+from .acquisition import evaluate_acquisitions
+from .bayesgpr import BayesGPR
+from .space import create_result, is_2Dlistlike, is_listlike, normalize_dimensions
+from .utils import construct_default_kernel
+
+__all__ = ["Optimizer", "r2_sequence"]
+
+ACQUISITION_FUNC = {
+    "ei": acquisition.ExpectedImprovement(),
+    "lcb": acquisition.LCB(),
+    "mean": acquisition.Expectation(),
+    "mes": acquisition.MaxValueSearch(),
+    "pvrs": acquisition.PVRS(),
+    "ts": acquisition.ThompsonSampling(),
+    "ttei": acquisition.TopTwoEI(),
+    "vr": acquisition.VarianceReduction(),
+}
+
+
+def _phi(d, n_iter=10):
+    if d == 1:
+        return 1.61803398874989484820458683436563
+    if d == 2:
+        return 1.32471795724474602596090885447809
+    x = 2.0
+    for _ in range(n_iter):
+        x = (1 + x) ** (1.0 / (d + 1.0))
+    return x
+
+
+def r2_sequence(n, d, seed=0.5):
+    """Additive-recurrence low-discrepancy sequence (Roberts' R_d), the reference's
+    ``init_strategy="r2"`` (bask/init.py:103-128)."""
+    g = _phi(d)
+    alpha = np.array([(1.0 / g) ** (j + 1) % 1 for j in range(d)])
+    return (seed + alpha[None, :] * (np.arange(n)[:, None] + 1)) % 1
+
+
+class Optimizer:
+    """Stepwise Bayesian optimisation with a fully Bayesian GP (see bask/optimizer.py:35-119 for
+    the parameters).  ``init_strategy="sb"`` is served by the R2 sequence here (the
+    Steinerberger design runs only before any GP exists and is outside the hot path)."""
+
+    def __init__(self, dimensions, n_points=500, n_initial_points=10, init_strategy="sb", gp_kernel=None,
+                 gp_kwargs=None, gp_priors=None, acq_func="pvrs", acq_func_kwargs=None, random_state=None,
+                 **kwargs):
+        self.rng = check_random_state(random_state)
+        if callable(acq_func):
+            self.acq_func = acq_func
+        else:
+            self.acq_func = ACQUISITION_FUNC[acq_func]
+        if acq_func_kwargs is None:
+            acq_func_kwargs = {}
+        self.acq_func_kwargs = acq_func_kwargs
+        self.space = normalize_dimensions(dimensions)
+        self._n_initial_points = n_initial_points
+        self.n_initial_points_ = n_initial_points
+        self.init_strategy = init_strategy
+        if self.init_strategy in ("r2", "sb"):
+            if self.init_strategy == "sb":
+                self._init_rng = np.random.RandomState(self.rng.randint(2 ** 31))
+            self._initial_points = self.space.inverse_transform(
+                r2_sequence(n=max(n_initial_points, 1), d=self.space.n_dims))
+        self.n_points = n_points
+        if gp_kwargs is None:
+            gp_kwargs = {}
+        if gp_kernel is None:
+            gp_kernel = construct_default_kernel(list(range(self.space.transformed_n_dims)))
+        self.gp = BayesGPR(kernel=gp_kernel, random_state=self.rng.randint(0, np.iinfo(np.int32).max),
+                           **gp_kwargs)
+        self.gp_priors = gp_priors
+        self.Xi = []
+        self.yi = []
+        self.noisei = []
+        self._next_x = None
+
+    def ask(self, n_points=1):
+        """Next point to evaluate (bask/optimizer.py:177-226)."""
+        if n_points > 1:
+            raise NotImplementedError("Returning multiple points is not implemented yet.")
+        if self._n_initial_points > 0:
+            if self.init_strategy in ("r2", "sb"):
+                return self._initial_points[self._n_initial_points - 1]
+            return self.space.rvs()[0]
+        if not self.gp.kernel_:
+            raise RuntimeError("Initialization is finished, but no model has been fit.")
+        return self._next_x
+
+    def tell(self, x, y, noise_vector=None, fit=True, replace=False, n_samples=0, gp_samples=100,
+             gp_burnin=10, progress=False):
+        """Adds observations, re-samples the hyper-posterior on device and computes the next
+        point (bask/optimizer.py:228-380)."""
+        if replace:
+            self.Xi = []
+            self.yi = []
+            self.noisei = []
+            self._n_initial_points = self.n_initial_points_
+        if is_listlike(y) and is_2Dlistlike(x):
+            self.Xi.extend(x)
+            self.yi.extend(y)
+            if noise_vector is None:
+                noise_vector = [0.0] * len(y)
+            elif not is_listlike(noise_vector) or len(noise_vector) != len(y):
+                raise ValueError("Vector of noise variances needs to be of equal length as `y`.")
+            self.noisei.extend(noise_vector)
+            self._n_initial_points -= len(y)
+        elif is_listlike(x):
+            self.Xi.append(x)
+            self.yi.append(y)
+            if noise_vector is None:
+                noise_vector = 0.0
+            elif is_listlike(noise_vector):
+                raise ValueError("Vector of noise variances is a list, while tell only received one datapoint.")
+            self.noisei.append(noise_vector)
+            self._n_initial_points -= 1
+        else:
+            raise ValueError(f"Type of arguments `x` ({type(x)}) and `y` ({type(y)}) not compatible.")
+
+        if fit and self._n_initial_points <= 0:
+            if self.gp_priors is not None and len(self.gp_priors) != self.space.transformed_n_dims + 2:
+                raise ValueError("The number of priors does not match the number of dimensions + 2.")
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                if self.gp.pos_ is None or replace:
+                    self.gp.fit(self.space.transform(self.Xi), self.yi, noise_vector=np.array(self.noisei),
+                                priors=self.gp_priors, n_desired_samples=gp_samples, n_burnin=gp_burnin,
+                                progress=progress)
+                else:
+                    self.gp.sample(self.space.transform(self.Xi), self.yi, noise_vector=np.array(self.noisei),
+                                   priors=self.gp_priors, n_desired_samples=gp_samples, n_burnin=gp_burnin,
+                                   progress=progress)
+            X = self.space.transform(self.space.rvs(n_samples=self.n_points, random_state=self.rng))
+            acq_values = evaluate_acquisitions(
+                X=X, gpr=self.gp, acquisition_functions=(self.acq_func,), n_samples=n_samples, progress=False,
+                random_state=self.rng.randint(0, np.iinfo(np.int32).max), **self.acq_func_kwargs).flatten()
+            self._next_x = self.space.inverse_transform(X[np.argmax(acq_values)].reshape((1, -1)))[0]
+        return create_result(self.Xi, self.yi, self.space, self.rng, models=[self.gp])
+
+    def run(self, func, n_iter=1, replace=False, n_samples=5, gp_samples=100, gp_burnin=10):
+        """ask -> func -> tell loop (bask/optimizer.py:382-445)."""
+        for _ in range(n_iter):
+            x = self.ask()
+            out = func(x)
+            if hasattr(out, "__len__"):
+                val, noise = out
+            else:
+                val = out
+                noise = 0.0
+            self.tell(x, val, noise_vector=noise, n_samples=n_samples, gp_samples=gp_samples,
+                      gp_burnin=gp_burnin, replace=replace)
+            replace = False
+        return create_result(self.Xi, self.yi, self.space, self.rng, models=[self.gp])

@@ -145,6 +145,20 @@ int bgp_dense_cholesky(bgp_handle_t h, const double* a_dev, int m, int64_t lda, 
 int bgp_slab_trmm(bgp_handle_t h, const double* slab_dev, int m, const double* e_dev, int ns,
                   const double* mean_dev, double* out_dev, void* stream);
 
+/* ---- full-GP acquisitions in Schur-complement form ------------------------------------
+ * The reference refactorises an (n+1)x(n+1) Gram matrix per candidate (PVRS
+ * bask/acquisition.py:328-339, VarianceReduction :285-300).  With v = L^-1 k(X, .) at the
+ * current theta (noise ON) the same number is
+ *   out[i] = sum_t |v_t|^2 + sum_t (k(t, x_i) - v_t . v_i)^2 / s_i,   s_i = k(x_i,x_i) - |v_i|^2
+ * PVRS: t runs over R Thompson points (dots_dev = v_t . v_i from bgp_predict_batched's extra
+ * right-hand sides, vt_dev = their whitened vectors, R x n).  VR: t runs over all candidates,
+ * with k(t,x_i) - v_t.v_i read from the noise-free posterior covariance (bgp_posterior_cov). */
+int bgp_pvrs_combine(bgp_handle_t h, const double* theta_dev, const double* xt_dev, int R,
+                     const double* xc_dev, int m, const double* dots_dev, const double* vt_dev,
+                     const double* s_dev, double* out_dev, void* stream);
+int bgp_vr_combine(bgp_handle_t h, const double* cov_dev, int m, int64_t ldc, const double* xc_dev,
+                   const double* theta_dev, const double* s_dev, double* out_dev, void* stream);
+
 /* ---- acquisition epilogues on (mu, sd), S x m -> m (bask/acquisition.py:112-141) ----
  * out[i] = (1/S) * sum over thetas whose row is entirely finite of acq(mu[s,:], sd[s,:])[i].
  * kind: registry strings of bask/optimizer.py:23-32.  p0: EI/TTEI y_opt (NaN = default

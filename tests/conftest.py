@@ -39,3 +39,8 @@ def g3():
 @pytest.fixture(scope="session")
 def g4():
     return load_golden("g4_kernel_zoo.npz")
+
+
+@pytest.fixture(scope="session")
+def g5():
+    return load_golden("g5_branin_long_chain.npz")

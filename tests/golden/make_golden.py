@@ -199,8 +199,18 @@ def g4():
     np.savez_compressed(os.path.join(HERE, "g4_kernel_zoo.npz"), **d)
 
 
+def g5():
+    """Long reference MCMC on config 1: posterior moments of theta for the distributional check."""
+    print("G5: long reference chain on config 1 (100 walkers x 300 steps after 100 burn-in)")
+    w = W.config1()
+    gp = fitted_reference_gp(w, n_desired=100 * 300, n_burnin=100, seed=11)
+    d = dict(chain_mean=gp.chain_.mean(axis=0), chain_std=gp.chain_.std(axis=0),
+             chain_len=np.array([len(gp.chain_)]), chain_thin=gp.chain_[::50].copy())
+    np.savez_compressed(os.path.join(HERE, "g5_branin_long_chain.npz"), **d)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["g1", "g2", "g3", "g4"]
+    which = sys.argv[1:] or ["g1", "g2", "g3", "g4", "g5"]
     for name in which:
         globals()[name]()
     for f in sorted(os.listdir(HERE)):

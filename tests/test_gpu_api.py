@@ -1,0 +1,222 @@
+"""GPU: the reference-facing Python surface (BayesGPR / evaluate_acquisitions / Optimizer) against
+the reference's golden vectors, its own tests' assertions, and distributional MCMC checks."""
+import numpy as np
+import pytest
+from sklearn.gaussian_process.kernels import RBF, ConstantKernel
+
+import bench_workloads as W
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def bask():
+    import bask_b200
+    return bask_b200
+
+
+def assert_acq_close(out, ref, name=""):
+    """Acquisition parity: 1e-8 relative (north star) wherever the value is within 1e-6 of the
+    sweep's maximum; in the deep tails (EI ~ 1e-90: d ln EI / dz = |z| > 5, so the value is an
+    ill-conditioned function of the 1e-10-accurate moments) 1e-5 relative."""
+    big = np.abs(ref) >= 1e-6 * np.abs(ref).max()
+    np.testing.assert_allclose(out[big], ref[big], rtol=1e-8, err_msg=name)
+    np.testing.assert_allclose(out[~big], ref[~big], rtol=1e-5, atol=1e-250, err_msg=name + " (tail)")
+    assert np.argmax(out) == np.argmax(ref), name
+
+
+def fitted_like_golden(bask, g, d, w):
+    """A BayesGPR whose data, chain and point estimate are the reference's (golden) ones."""
+    gp = bask.BayesGPR(kernel=bask.construct_default_kernel(list(range(d))), normalize_y=True, random_state=0)
+    gp.fit(w.X, w.y, noise_vector=w.noise_vector, n_desired_samples=w.n_walkers, n_burnin=0,
+           n_walkers_per_thread=w.n_walkers, progress=False)
+    np.testing.assert_allclose(gp.y_train_, g["y_train"], rtol=1e-12)
+    gp.chain_ = g["chain"].copy()
+    gp.theta = g["theta_median"]
+    return gp
+
+
+def test_sweep_matches_reference_rng_flow(bask, g1):
+    """evaluate_acquisitions with the reference's chain: identical theta picks and Gumbel draws,
+    values within 1e-8, identical argmax (BASELINE.json north_star)."""
+    w = W.config1()
+    gp = fitted_like_golden(bask, g1, 2, w)
+    acqs = [bask.ExpectedImprovement(), bask.TopTwoEI(), bask.LCB(), bask.Expectation(), bask.MaxValueSearch()]
+    np.random.seed(w.mes_seed)
+    out = bask.evaluate_acquisitions(g1["Xc"], gp, acqs, n_samples=10, random_state=1)
+    for j, name in enumerate(("ei", "ttei", "lcb", "mean", "mes")):
+        assert_acq_close(out[j], g1[f"sweep_{name}"], name)
+    # the estimator is left untouched by the sweep
+    np.testing.assert_array_equal(gp.theta, g1["theta_median"])
+
+
+def test_sweep_headline_shape(bask, g3):
+    w = W.config3(m=1500)
+    gp = fitted_like_golden(bask, g3, 6, w)
+    np.random.seed(w.mes_seed)
+    out = bask.evaluate_acquisitions(g3["Xc"], gp, [bask.MaxValueSearch(), bask.ExpectedImprovement()],
+                                     n_samples=3, random_state=1)
+    for j, name in enumerate(("mes", "ei")):
+        assert_acq_close(out[j], g3[f"sweep_{name}"], name)
+
+
+def test_estimator_attributes_and_predict(bask, g1):
+    w = W.config1()
+    gp = fitted_like_golden(bask, g1, 2, w)
+    np.testing.assert_allclose(gp.L_, g1["L_median"], rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(gp.alpha_, g1["alpha_median"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(gp.K_inv_, g1["K_inv_median"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(gp.log_marginal_likelihood(g1["thetas"][0]), g1["lml"][0], rtol=1e-9)
+    gp.theta = g1["thetas"][0]
+    mu, sd = gp.predict(g1["Xc"], return_std=True)
+    np.testing.assert_allclose(sd, g1["std_noisy"], rtol=1e-8)
+    with gp.noise_set_to_zero():
+        mu0, sd0 = gp.predict(g1["Xc"], return_std=True)
+    np.testing.assert_allclose(mu0, g1["mu"][0], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(sd0, g1["std"][0], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(gp.predict(g1["Xc"], return_std=True)[1], g1["std_noisy"], rtol=1e-8)
+    # with_hyperparam restores the previous point estimate
+    before = gp.theta
+    with gp.with_hyperparam(g1["thetas"][3]):
+        np.testing.assert_allclose(gp.theta, g1["thetas"][3])
+    np.testing.assert_array_equal(gp.theta, before)
+    gp.theta = g1["theta_median"]
+    with gp.noise_set_to_zero():
+        mu_c, cov_c = gp.predict(g1["Xc"][:48], return_cov=True)
+    np.testing.assert_allclose(mu_c, g1["post_mean48"], rtol=1e-8)
+    np.testing.assert_allclose(cov_c, g1["post_cov48"], rtol=1e-6, atol=1e-9)
+
+
+def test_full_gp_acquisitions(bask, g1, g2):
+    gp = fitted_like_golden(bask, g1, 2, W.config1())
+    vr = bask.VarianceReduction()(g1["Xc"][:200], gp)
+    np.testing.assert_allclose(vr, g1["vr"], rtol=1e-7)
+    pv = bask.PVRS()(g1["Xc"], gp, thompson_idx=g1["pvrs_thompson_idx"])
+    np.testing.assert_allclose(pv, g1["pvrs"], rtol=1e-7)
+    assert np.argmax(pv) == np.argmax(g1["pvrs"])
+    gp2 = fitted_like_golden(bask, g2, 6, W.config2())
+    pv2 = bask.PVRS()(g2["Xc"], gp2, thompson_idx=g2["pvrs_thompson_idx"])
+    np.testing.assert_allclose(pv2, g2["pvrs"], rtol=1e-7)
+    assert np.argmax(pv2) == np.argmax(g2["pvrs"])
+    vr2 = bask.VarianceReduction()(g2["Xc"][:100], gp2)
+    np.testing.assert_allclose(vr2, g2["vr"], rtol=1e-7)
+    # free-running PVRS (own Thompson draws) is finite and positive
+    out = bask.evaluate_acquisitions(g2["Xc"], gp2, [bask.PVRS()], n_samples=0, random_state=3, n_thompson=10)
+    assert out.shape == (1, 1000) and np.all(np.isfinite(out)) and np.all(out > 0)
+
+
+def test_joint_draws_distribution(bask, g1):
+    """sample_y draws follow N(mean, cov) of the reference's posterior (Cholesky instead of SVD)."""
+    gp = fitted_like_golden(bask, g1, 2, W.config1())
+    Xs = g1["Xc"][:48]
+    draws = gp.sample_y(Xs, sample_mean=True, n_samples=4000, random_state=0)
+    assert draws.shape == (48, 4000)
+    sd = np.sqrt(np.diag(g1["post_cov48"]))
+    np.testing.assert_allclose(draws.mean(axis=1), g1["post_mean48"], atol=5 * sd.max() / np.sqrt(4000))
+    emp = np.cov(draws)
+    assert np.abs(emp - g1["post_cov48"]).max() < 0.15 * sd.max() ** 2
+    one = gp.sample_y(Xs, n_samples=3, random_state=1)
+    assert one.shape == (48, 3) and np.all(np.isfinite(one))
+    ts = bask.evaluate_acquisitions(Xs, gp, [bask.ThompsonSampling()], n_samples=2, random_state=0)
+    assert ts.shape == (1, 48) and np.all(np.isfinite(ts))
+
+
+def test_mcmc_posterior_matches_reference_chain(bask, g5):
+    """Device stretch move vs the reference's emcee chain on config 1: posterior means of theta
+    agree within Monte-Carlo error (different RNG, same target)."""
+    w = W.config1()
+    gp = bask.BayesGPR(kernel=bask.construct_default_kernel([0, 1]), normalize_y=True, random_state=3)
+    gp.fit(w.X, w.y, noise_vector=w.noise_vector, n_desired_samples=100 * 400, n_burnin=200,
+           n_walkers_per_thread=100, progress=False)
+    assert gp.chain_.shape == (40000, 4)
+    mean, std = gp.chain_.mean(axis=0), gp.chain_.std(axis=0)
+    np.testing.assert_allclose(mean, g5["chain_mean"], atol=0.12 * g5["chain_std"].max())
+    np.testing.assert_allclose(std, g5["chain_std"], rtol=0.15)
+    assert 0.2 < gp._acceptance.mean() < 0.8
+
+
+# ---- the reference's own behavioural tests (tests/test_bayesgpr.py, tests/test_optimizer.py) ----
+@pytest.fixture
+def minimal_gp(bask):
+    kernel = ConstantKernel(constant_value=1 ** 2, constant_value_bounds=(0.01 ** 2, 1 ** 2)) * RBF(
+        length_scale=1.0, length_scale_bounds=(0.5, 1.5))
+    return bask.BayesGPR(random_state=1, normalize_y=False, kernel=kernel)
+
+
+@pytest.fixture
+def minimal_priors():
+    from scipy.stats import halfnorm, invgamma
+    return [lambda x: halfnorm(scale=1.0).logpdf(np.sqrt(np.exp(x))) + x / 2.0 - np.log(2.0),
+            lambda x: invgamma(a=5.0, scale=1.0).logpdf(np.exp(x)) + x,
+            lambda x: halfnorm(scale=1.0).logpdf(np.sqrt(np.exp(x))) + x / 2.0 - np.log(2.0)]
+
+
+def test_noise_vector(minimal_gp, minimal_priors):
+    X = np.array([[0.0], [0.0]])
+    y = np.array([1.0, 0.0])
+    minimal_gp.fit(X, y, noise_vector=np.array([1234, 0.0]), n_burnin=1, progress=False, priors=minimal_priors)
+    assert minimal_gp.predict(np.array([[0.0]])) < 0.01
+
+
+def test_noise_set_to_zero(minimal_gp, minimal_priors):
+    X = np.array([[0.1], [0.0], [-0.1]])
+    y = np.array([0.0, 0.0, 0.0])
+    minimal_gp.fit(X, y, n_burnin=1, progress=False, priors=minimal_priors)
+    minimal_gp.theta = np.array([0.0, 0.0, 0.0])
+    assert minimal_gp.predict(np.array([[0.0]]), return_std=True)[1] >= 1.0
+    with minimal_gp.noise_set_to_zero():
+        assert minimal_gp.predict(np.array([[0.0]]), return_std=True)[1] < 1.0
+    assert minimal_gp.predict(np.array([[0.0]]), return_std=True)[1] >= 1.0
+
+
+def test_typed_priors_equal_python_callables(bask, minimal_gp, minimal_priors):
+    """The host-stepped sampler (arbitrary Python priors) and the all-device sampler (typed
+    priors) evaluate the same log posterior."""
+    from bask_b200.priors import HalfNormalSqrtPrior, InvGammaPrior
+    X = np.array([-2.0, -1.0, 1.0, 2.0])[:, None]
+    y = np.array([0.0, -1.0, 1.0, 2.0])
+    minimal_gp.fit(X, y, priors=minimal_priors, progress=False, n_burnin=1)
+    typed = [HalfNormalSqrtPrior(1.0), InvGammaPrior(5.0, 1.0), HalfNormalSqrtPrior(1.0)]
+    th = minimal_gp.chain_[:16]
+    a = minimal_gp._log_prob_fn(th, minimal_priors)
+    b = minimal_gp._log_prob_fn(th, typed)
+    np.testing.assert_allclose(a, b, rtol=1e-10)
+
+
+def test_sample_without_fit(minimal_gp):
+    with pytest.raises(ValueError):
+        minimal_gp.sample()
+
+
+def test_optimizer_loop(bask):
+    opt = bask.Optimizer(dimensions=[(-2.0, 2.0)], n_initial_points=1, random_state=0)
+    opt.run(lambda x: x[0] ** 2, n_iter=3, gp_burnin=0, n_samples=1)
+    assert len(opt.Xi) == 3
+    opt.ask()
+    assert len(opt.Xi) == 3
+    assert opt.ask() == opt.ask()
+
+
+def test_optimizer_noise_vector_and_errors(bask):
+    opt = bask.Optimizer(dimensions=[(-2.0, 2.0)], n_initial_points=5, random_state=1)
+    opt.tell([[-2.0], [-1.0], [0.0], [1.0], [2.0]], [0.0, -1.0, 0.0, -1.0, 0.0],
+             noise_vector=[1.0, 1.0, 1.0, 0.0, 1.0])
+    y_noisy, y = opt.gp.predict([[0.25], [0.75]])
+    assert y_noisy > y
+    assert np.iterable(opt.gp.alpha)
+    bad = bask.Optimizer(dimensions=[(-2.0, 2.0)], n_initial_points=0, gp_priors=[lambda x: -x ** 2])
+    with pytest.raises(ValueError):
+        bad.tell([[0.0], [1.0]], [0.0, 1.0])
+
+
+@pytest.mark.parametrize("acq", ["ei", "lcb", "mean", "mes", "pvrs", "ts", "ttei", "vr"])
+def test_optimizer_every_acquisition(bask, acq):
+    opt = bask.Optimizer(dimensions=[(0.0, 1.0), (0.0, 1.0)], n_points=200, n_initial_points=6, acq_func=acq,
+                         random_state=2)
+    f = lambda x: (x[0] - 0.3) ** 2 + (x[1] - 0.6) ** 2   # noqa: E731
+    for _ in range(6):
+        x = opt.ask()
+        opt.tell(x, f(x), fit=False)
+    opt.tell([0.5, 0.5], f([0.5, 0.5]), n_samples=2, gp_samples=100, gp_burnin=2)
+    nxt = opt.ask()
+    assert len(nxt) == 2 and all(0.0 <= v <= 1.0 for v in nxt)
