@@ -55,6 +55,8 @@ struct bgp_handle_s {
   cudaGraphExec_t graph = nullptr;
   GraphKey key;
   bool have_graph = false;
+  long long* dbg = nullptr;   // developer tooling: clock stamps of the factorisation kernel
+  int dbg_tid = 0;
 };
 
 #define CHECK_H(h) if (!(h)) return fail("null handle")
@@ -129,6 +131,11 @@ int bgp_set_kernel(bgp_handle_t h, const bgp_op_t* ops, int n_ops, int n_theta, 
   }
   if (depth != 1) return fail("malformed postfix program");
   P.n_leaves = leaves;
+  if (n_ops == 5 && ops[0].code == BGP_OP_CONST && ops[1].code >= BGP_OP_RBF && ops[1].code <= BGP_OP_MATERN52 &&
+      ops[2].code == BGP_OP_MUL && ops[3].code == BGP_OP_WHITE && ops[4].code == BGP_OP_ADD) {
+    P.fast_kind = ops[1].code; P.fast_const = 0; P.fast_white = 3;
+    P.fast_white_zeroable = (ops[3].flags & BGP_FLAG_ZEROABLE_WHITE) ? 1 : 0;
+  }
   P.d = h->d;
   if (n_fixed_ls > 0) {
     CUDA_TRY(h->fixed_ls.ensure(sizeof(double) * n_fixed_ls));
@@ -139,7 +146,7 @@ int bgp_set_kernel(bgp_handle_t h, const bgp_op_t* ops, int n_ops, int n_theta, 
   h->have_prog = true;
   h->have_graph = false;
   if (h->have_data) {
-    cudaError_t e = bgp::prepare_chol(h->n, h->d, leaves, false);
+    cudaError_t e = bgp::prepare_chol(h->n);
     if (e != cudaSuccess) return fail("n/d too large for the shared-memory plan of the factorisation kernel", e);
   }
   return 0;
@@ -173,7 +180,7 @@ int bgp_set_data(bgp_handle_t h, const double* X_dev, const double* y_dev, const
   if (h->n != n || h->d != d) h->have_graph = false;
   h->n = n; h->d = d;
   {
-    cudaError_t e = bgp::prepare_chol(n, d, h->have_prog ? h->host_prog.n_leaves : 1, false);
+    cudaError_t e = bgp::prepare_chol(n);
     if (e != cudaSuccess) return fail("n/d too large for the shared-memory plan of the factorisation kernel", e);
   }
   if (h->have_prog && h->host_prog.d != d) {
@@ -192,25 +199,43 @@ static int ready(bgp_handle_t h) {
   return 0;
 }
 
+static int slots_for(bgp_handle_t h) { return h->n <= 64 ? 2 * h->sms : h->sms; }
+
+static int ensure_logprob_workspace(bgp_handle_t h) {
+  const SlabGeom G = SlabGeom::make(h->n, false);
+  const int slots = slots_for(h);
+  CUDA_TRY(h->slabs_scratch.ensure(sizeof(double) * (size_t)G.doubles() * slots));
+  CUDA_TRY(h->xt_scratch.ensure(sizeof(double) * bgp::gram_xt_doubles(h->n, h->d, h->host_prog.n_leaves) * slots));
+  return 0;
+}
+
+// K1 (Gram, all SMs) then K2 (factorisation, one CTA per theta), in waves of one slab per SM
 static int logprob_impl(bgp_handle_t h, const double* theta_dev, int batch, const double* lp_extra_dev,
                         double* lp_dev, double* lml_dev, int32_t* info_dev, cudaStream_t st) {
-  const SlabGeom G = SlabGeom::make(h->n, false);
-  const int slots = h->n <= 64 ? 2 * h->sms : h->sms;
-  CUDA_TRY(h->slabs_scratch.ensure(sizeof(double) * (size_t)G.doubles() * slots));
-  bgp::CholArgs A;
-  A.X = h->X.as<double>(); A.y = h->y.as<double>(); A.alpha = h->alpha.as<double>();
-  A.theta = theta_dev; A.lp_extra = lp_extra_dev; A.lp = lp_dev; A.lml = lml_dev; A.info = info_dev;
-  A.slabs = h->slabs_scratch.as<double>(); A.z_out = nullptr;
-  A.prog = h->prog.as<DevProgram>(); A.fixed_ls = h->fixed_ls.as<double>();
-  A.priors = h->have_priors ? h->priors.as<bgp_prior_t>() : nullptr; A.n_priors = h->n_priors;
-  A.n = h->n; A.d = h->d; A.batch = batch; A.aug = 0; A.slab_per_block = 1;
-  A.dense = nullptr; A.ldd = 0; A.jitter = 0.0;
-  A.xt_scratch = nullptr; A.xt_stride = 0;
-  if (size_t xt = bgp::chol_xt_scratch_doubles(h->n, h->d, h->host_prog.n_leaves)) {
-    CUDA_TRY(h->xt_scratch.ensure(sizeof(double) * xt * slots));
-    A.xt_scratch = h->xt_scratch.as<double>(); A.xt_stride = (long long)xt;
+  if (ensure_logprob_workspace(h)) return -1;
+  const int slots = slots_for(h), p = h->host_prog.n_theta;
+  const size_t xt = bgp::gram_xt_doubles(h->n, h->d, h->host_prog.n_leaves);
+  for (int b0 = 0; b0 < batch; b0 += slots) {
+    const int nb = batch - b0 < slots ? batch - b0 : slots;
+    bgp::GramArgs Gm{h->X.as<double>(), h->alpha.as<double>(), theta_dev + (size_t)b0 * p,
+                     h->slabs_scratch.as<double>(), h->xt_scratch.as<double>(), (long long)xt,
+                     h->prog.as<DevProgram>(), h->fixed_ls.as<double>(), h->n, h->d, nb, 0};
+    CUDA_TRY(bgp::launch_gram(Gm, st));
+    bgp::CholArgs A;
+    std::memset(&A, 0, sizeof(A));
+    A.X = h->X.as<double>(); A.y = h->y.as<double>(); A.alpha = h->alpha.as<double>();
+    A.theta = theta_dev + (size_t)b0 * p;
+    A.lp_extra = lp_extra_dev ? lp_extra_dev + b0 : nullptr;
+    A.lp = lp_dev ? lp_dev + b0 : nullptr;
+    A.lml = lml_dev ? lml_dev + b0 : nullptr;
+    A.info = info_dev ? info_dev + b0 : nullptr;
+    A.slabs = h->slabs_scratch.as<double>();
+    A.prog = h->prog.as<DevProgram>(); A.fixed_ls = h->fixed_ls.as<double>();
+    A.priors = h->have_priors ? h->priors.as<bgp_prior_t>() : nullptr; A.n_priors = h->n_priors;
+    A.n = h->n; A.d = h->d; A.batch = nb; A.aug = 0; A.slab_per_block = 0;
+    A.dbg = h->dbg; A.dbg_tid = h->dbg_tid;
+    CUDA_TRY(bgp::launch_chol(A, nb, st));
   }
-  CUDA_TRY(bgp::launch_chol(A, batch < slots ? batch : slots, h->host_prog.n_leaves, st));
   return 0;
 }
 
@@ -224,6 +249,14 @@ int bgp_logprob_batched(bgp_handle_t h, const double* theta_dev, int batch, cons
   return logprob_impl(h, theta_dev, batch, lp_extra_dev, lp_dev, lml_dev, info_dev, (cudaStream_t)stream);
 }
 
+/* developer tooling (not in include/bgp.h): device buffer of 8 clock64 stamps per panel */
+int bgp_debug_set_stamps(bgp_handle_t h, long long* stamps_dev, int tid) {
+  CHECK_H(h);
+  h->dbg = stamps_dev;
+  h->dbg_tid = tid;
+  return 0;
+}
+
 int64_t bgp_factor_slab_doubles(bgp_handle_t h) {
   if (!h || !h->have_data) return -1;
   return SlabGeom::make(h->n, true).doubles();
@@ -235,20 +268,19 @@ int bgp_factorize_batched(bgp_handle_t h, const double* theta_dev, int S, double
   if (ready(h)) return -1;
   if (!theta_dev || S <= 0 || !slabs_dev || !z_dev) return fail("bad factorize arguments");
   CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t xt = bgp::gram_xt_doubles(h->n, h->d, h->host_prog.n_leaves);
+  CUDA_TRY(h->xt_scratch.ensure(sizeof(double) * xt * (size_t)(S > slots_for(h) ? S : slots_for(h))));
+  bgp::GramArgs Gm{h->X.as<double>(), h->alpha.as<double>(), theta_dev, slabs_dev, h->xt_scratch.as<double>(),
+                   (long long)xt, h->prog.as<DevProgram>(), h->fixed_ls.as<double>(), h->n, h->d, S, 1};
+  CUDA_TRY(bgp::launch_gram(Gm, st));
   bgp::CholArgs A;
+  std::memset(&A, 0, sizeof(A));
   A.X = h->X.as<double>(); A.y = h->y.as<double>(); A.alpha = h->alpha.as<double>();
-  A.theta = theta_dev; A.lp_extra = nullptr; A.lp = nullptr; A.lml = lml_dev; A.info = info_dev;
-  A.slabs = slabs_dev; A.z_out = z_dev;
+  A.theta = theta_dev; A.lml = lml_dev; A.info = info_dev; A.slabs = slabs_dev; A.z_out = z_dev;
   A.prog = h->prog.as<DevProgram>(); A.fixed_ls = h->fixed_ls.as<double>();
-  A.priors = nullptr; A.n_priors = 0;
   A.n = h->n; A.d = h->d; A.batch = S; A.aug = 1; A.slab_per_block = 0;
-  A.dense = nullptr; A.ldd = 0; A.jitter = 0.0;
-  A.xt_scratch = nullptr; A.xt_stride = 0;
-  if (size_t xt = bgp::chol_xt_scratch_doubles(h->n, h->d, h->host_prog.n_leaves)) {
-    CUDA_TRY(h->xt_scratch.ensure(sizeof(double) * xt * S));
-    A.xt_scratch = h->xt_scratch.as<double>(); A.xt_stride = (long long)xt;
-  }
-  CUDA_TRY(bgp::launch_chol(A, S, h->host_prog.n_leaves, (cudaStream_t)stream));
+  CUDA_TRY(bgp::launch_chol(A, S, st));
   return 0;
 }
 
@@ -334,13 +366,13 @@ int bgp_dense_cholesky(bgp_handle_t h, const double* a_dev, int m, int64_t lda, 
   CHECK_H(h);
   if (!a_dev || m <= 0 || lda < m || !slab_dev || !info_dev) return fail("bad dense-cholesky arguments");
   CUDA_TRY(cudaSetDevice(h->device));
-  CUDA_TRY(bgp::prepare_chol(m, 1, 0, true));
+  CUDA_TRY(bgp::prepare_chol(m));
   bgp::CholArgs A;
   std::memset(&A, 0, sizeof(A));
   A.slabs = slab_dev; A.info = info_dev; A.n = m; A.d = 1; A.batch = 1; A.aug = 0; A.slab_per_block = 0;
   A.dense = a_dev; A.ldd = lda; A.jitter = jitter;
-  CUDA_TRY(bgp::launch_chol(A, 1, 0, (cudaStream_t)stream));
-  if (h->have_data) CUDA_TRY(bgp::prepare_chol(h->n, h->d, h->host_prog.n_leaves, false));
+  CUDA_TRY(bgp::launch_chol(A, 1, (cudaStream_t)stream));
+  if (h->have_data) CUDA_TRY(bgp::prepare_chol(h->n));
   return 0;
 }
 
@@ -454,13 +486,7 @@ int bgp_mcmc_run(bgp_handle_t h, double* pos_dev, double* lp_dev, int W, int T, 
   CUDA_TRY(h->mc_q.ensure(sizeof(double) * W * p));
   CUDA_TRY(h->mc_factors.ensure(sizeof(double) * W));
   CUDA_TRY(h->mc_newlp.ensure(sizeof(double) * W));
-  {  // workspace of the log-posterior kernel must exist before capture starts
-    const SlabGeom G = SlabGeom::make(h->n, false);
-    const int slots = h->n <= 64 ? 2 * h->sms : h->sms;
-    CUDA_TRY(h->slabs_scratch.ensure(sizeof(double) * (size_t)G.doubles() * slots));
-    if (size_t xt = bgp::chol_xt_scratch_doubles(h->n, h->d, h->host_prog.n_leaves))
-      CUDA_TRY(h->xt_scratch.ensure(sizeof(double) * xt * slots));
-  }
+  if (ensure_logprob_workspace(h)) return -1;   // must exist before capture starts
   *h->seed_pinned = seed;
   CUDA_TRY(cudaMemcpyAsync(h->mc_seed.p, h->seed_pinned, sizeof(uint64_t), cudaMemcpyHostToDevice, st));
   if (st == nullptr) {  // the legacy default stream cannot be captured: run eagerly

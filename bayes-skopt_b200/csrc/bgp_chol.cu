@@ -1,8 +1,7 @@
 // K1+K2: batched-theta Gram build + FP64 Cholesky + forward solve + LML + log-prior,
 // one CTA per theta.  Left-looking blocked factorisation, 32-column panels:
-//   * the Gram panel is generated from X by the CTA itself right before it is factored
-//     (fused K1) into the L2-resident factor slab -- the n x n matrix never exists in HBM as
-//     an input;
+//   * the Gram matrix arrives in the L2-resident factor slab, written by the K1 kernel of the
+//     same stream (bgp_gram.cu) in exactly the tiled layout consumed here;
 //   * trailing updates and the panel triangular solve are DMMA.8x8x4 GEMMs whose A operand
 //     streams from the slab in 16-byte loads, B operand is staged in shared memory;
 //   * y rides along as one extra row, so z = L^-1 y (and y^T K^-1 y = |z|^2) falls out of the
@@ -16,8 +15,8 @@
 namespace bgp {
 
 constexpr int KCH = 15;        // previous panels staged in shared memory at once
-constexpr int WS = 40;         // row stride of the 32x32 inverse block (== 8 mod 16)
-constexpr int PS = 33;         // row stride of the diagonal block (odd: conflict-free columns)
+constexpr int LS = 40;         // row stride of the factored diagonal block read by DMMA (== 8 mod 16)
+constexpr int PS = 33;         // row stride of the diagonal block being factored (odd: conflict-free)
 constexpr int PP = 34;         // row stride of the K-split partial blocks
 
 template <int NW>
@@ -25,10 +24,10 @@ struct CholSmem {
   DevProgram prog;
   ThetaParams tp;
   double Dblk[32 * PS];              // diagonal block being factored
-  double Ws[32 * WS];                // its inverse
+  double Lt[32 * LS];                // factored block L_kk, DMMA-friendly stride
+  double Wd[4][8 * 8];               // inverses of its four 8x8 diagonal sub-blocks
   double Part[4][32 * PP];           // K-split partial sums of the diagonal update
   double red[NW];
-  double inv_diag[32];
   int fail;
 };
 
@@ -59,91 +58,245 @@ __device__ __forceinline__ double log_prior(const bgp_prior_t* pr, int n, const 
   return lp;
 }
 
-// ---- warp-level Cholesky + inverse of the 32x32 diagonal block in shared memory ----------
-// Compact (rolled) code on purpose: it runs once per panel on one warp, so straight-line
-// unrolled code would be instruction-fetch bound.  Returns 0 or failing local column + 1
-// (LAPACK dpotrf: pivot <= 0 or NaN).
-__device__ __noinline__ int warp_potrf_inv32(double* D, double* Ws, double* inv_diag, int lane,
-                                             double& logdet, int ncols_real) {
+// ---- warp-level Cholesky of the 32x32 diagonal block + inverses of its 8x8 diagonal blocks --
+// Lane i owns row i.  Columns are processed in blocks of eight held in registers: a rolled
+// left-looking update from the previous column blocks (shared memory), then an unrolled
+// in-register factorisation of the eight columns with shuffles, so the per-column critical
+// path is shuffle -> rsqrt -> scale -> shuffle -> fma.  The panel solve only needs the four
+// 8x8 inverses (block forward substitution on DMMA), computed at the end by all lanes at once.
+// Returns 0 or failing local column + 1 (LAPACK dpotrf: pivot <= 0 or NaN).
+__device__ __noinline__ int warp_potrf32(double* __restrict__ D, double* __restrict__ Lt,
+                                         double* __restrict__ Wd, int lane, double& logdet, int ncols_real) {
   int fail = 0;
-  for (int j = 0; j < 32; ++j) {
-    double ajj = D[j * PS + j];
-    if (!(ajj > 0.0)) { if (!fail) fail = j + 1; ajj = 1.0; }
-    const double ljj = sqrt(ajj);
-    const double inv = 1.0 / ljj;
-    const double v = D[lane * PS + j];
-    const double lij = lane > j ? v * inv : (lane == j ? ljj : 0.0);
-    __syncwarp();
-    D[lane * PS + j] = lij;
-    if (lane == j) inv_diag[j] = inv;
-    __syncwarp();
-#pragma unroll 4
-    for (int k = j + 1; k < 32; ++k) {
-      const double lkj = D[k * PS + j];
-      if (lane >= k) D[lane * PS + k] = fma(-lij, lkj, D[lane * PS + k]);
+  double* __restrict__ myrow = D + lane * PS;
+  double my_inv = 1.0, w[8];
+  for (int b = 0; b < 4; ++b) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) w[c] = myrow[8 * b + c];
+    for (int k = 0; k < 8 * b; ++k) {
+      const double lik = myrow[k];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) w[c] = fma(-lik, D[(8 * b + c) * PS + k], w[c]);
     }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int j = 8 * b + c;
+      double ajj = __shfl_sync(0xffffffffu, w[c], j);
+      if (!(ajj > 0.0)) { if (!fail) fail = j + 1; ajj = 1.0; }
+      const double inv = rsqrt(ajj);
+      const double lij = lane > j ? w[c] * inv : (lane == j ? ajj * inv : 0.0);
+      if (lane == j) my_inv = inv;
+      w[c] = lij;
+#pragma unroll
+      for (int c2 = c + 1; c2 < 8; ++c2) {
+        const double lkj = __shfl_sync(0xffffffffu, lij, 8 * b + c2);
+        w[c2] = fma(-lij, lkj, w[c2]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) myrow[8 * b + c] = w[c];
     __syncwarp();
   }
-  if (lane < ncols_real) logdet += log(D[lane * PS + lane]);
-  // W = L^-1: lane c solves column c by forward substitution (4 partial sums break the chain)
-  for (int i = 0; i < 32; ++i) {
-    double s0 = (i == lane) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int k = 0;
-    for (; k + 4 <= i; k += 4) {
-      s0 = fma(-D[i * PS + k], Ws[k * WS + lane], s0);
-      s1 = fma(-D[i * PS + k + 1], Ws[(k + 1) * WS + lane], s1);
-      s2 = fma(-D[i * PS + k + 2], Ws[(k + 2) * WS + lane], s2);
-      s3 = fma(-D[i * PS + k + 3], Ws[(k + 3) * WS + lane], s3);
+  if (lane < ncols_real) logdet -= log(my_inv);
+  // after the loop w[] holds this lane's entries of column block 3; reload the diagonal block
+  // row of this lane's own 8x8 sub-block: lanes 8g..8g+7 hold L_gg row-wise
+  const int g = lane >> 3, ci = lane & 7;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) w[c] = myrow[8 * g + c];
+  // column ci of W_gg = L_gg^-1 by forward substitution; L_gg[i][k] lives in lane 8g+i, w[k]
+  double x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    double sacc = (i == ci) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < i; ++k) {
+      const double lik = __shfl_sync(0xffffffffu, w[k], i, 8);
+      sacc = fma(-lik, x[k], sacc);
     }
-    for (; k < i; ++k) s0 = fma(-D[i * PS + k], Ws[k * WS + lane], s0);
-    Ws[i * WS + lane] = (i >= lane) ? ((s0 + s1) + (s2 + s3)) * inv_diag[i] : 0.0;
+    const double dinv = __shfl_sync(0xffffffffu, my_inv, i, 8);
+    x[i] = (i >= ci) ? sacc * dinv : 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) Wd[g * 64 + i * 8 + ci] = x[i];
+  // DMMA-friendly copy of L_kk (zeros above the diagonal)
+  for (int e = lane; e < 1024; e += 32) {
+    const int rr = e >> 5, cc = e & 31;
+    Lt[rr * LS + cc] = cc <= rr ? D[rr * PS + cc] : 0.0;
   }
   __syncwarp();
   return fail;
 }
 
-// Gram entries of panel k (rows [32k, n) x 32 columns, lower part) -> slab.  Each warp takes
-// four rows at a time, lanes are the 32 columns; scaled coordinates come from the transposed
-// shared-memory copy Xt[leaf][dim][npad] (conflict-free for lanes, broadcast for rows).
-template <int NW>
-__device__ __forceinline__ void gram_panel(const DevProgram& PR, const ThetaParams& TP, const double* Xt,
-                                           int npad, const double* __restrict__ alpha, double* slab,
-                                           const SlabGeom& G, int k, int n, int d, int warp, int lane) {
-  const int c0 = 32 * k, col = c0 + lane;
-  double* base = slab + G.off(k);
-  for (int r0 = c0 + 4 * warp; r0 < n; r0 += 4 * NW) {
-    double r2[4][BGP_MAX_LEAVES];
+// stage rows [c0, c0+32) x the columns of panels [j0, j0+kc) of L into shared memory
+__device__ __forceinline__ void stage_block_row(const double* slab, const SlabGeom& G, double* Bs, int bstride,
+                                                int c0, int j0, int kc, int tid, int nthreads) {
+  // four independent 16-byte loads in flight per thread before the first store
+  for (int idx0 = tid; idx0 < 512 * kc; idx0 += 4 * nthreads) {
+    double2 v[4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int l = 0; l < BGP_MAX_LEAVES; ++l) r2[a][l] = 0.0;
-#pragma unroll
-    for (int l = 0; l < BGP_MAX_LEAVES; ++l) {
-      if (l < PR.n_leaves) {
-        const double* xl = Xt + (size_t)l * d * npad;
-        for (int kk = 0; kk < d; ++kk) {
-          const double* xr = xl + (size_t)kk * npad;
-          const double xc = xr[col];
-#pragma unroll
-          for (int a = 0; a < 4; ++a) {
-            const double t = xr[min(r0 + a, npad - 1)] - xc;
-            r2[a][l] = fma(t, t, r2[a][l]);
-          }
-        }
+    for (int s = 0; s < 4; ++s) {
+      const int idx = idx0 + s * nthreads;
+      if (idx < 512 * kc) {
+        const int c2 = idx & 15, row = (idx >> 4) & 31, jj = idx >> 9;
+        v[s] = *reinterpret_cast<const double2*>(
+            slab + G.off(j0 + jj) + (size_t)(c0 + row - 32 * (j0 + jj)) * 32 + 2 * c2);
       }
     }
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int row = r0 + a;
-      if (row < n && col <= row) {
-        const bool same = row == col;
-        if (same) {
+    for (int s = 0; s < 4; ++s) {
+      const int idx = idx0 + s * nthreads;
+      if (idx < 512 * kc) {
+        const int c2 = idx & 15, row = (idx >> 4) & 31, jj = idx >> 9;
+        *reinterpret_cast<double2*>(Bs + (size_t)row * bstride + 32 * jj + 2 * c2) = v[s];
+      }
+    }
+  }
+}
+
+struct TileSet {
+  int rb[4];     // first storage row of each 8-row tile
+  int kind[4];   // 0 training rows, 1 the y row, 2 identity rows, 3 unused slot
+  int js[4];     // first previous panel with non-zero entries (identity rows only)
+};
+
+// acc[t][u] += A_t (8 x 32*kc, streamed from the slab) * B_u^T (shared memory) for the NTL tiles
+// of this warp.  NTL is a template parameter on purpose: predicated-off DMMAs still occupy the
+// FP64 pipe, so inactive tiles must not appear in the instruction stream at all.
+template <int NTL>
+__device__ __forceinline__ void k_chunk(double (&acc)[4][4][2], const TileSet& TS, const double* slab,
+                                        const SlabGeom& G, const double* Bs, int bstride, int j0, int kc,
+                                        int r, int q) {
+  int jmin = j0 + kc;
 #pragma unroll
-          for (int l = 0; l < BGP_MAX_LEAVES; ++l) r2[a][l] = 0.0;
+  for (int t = 0; t < NTL; ++t) jmin = min(jmin, TS.js[t]);
+  const int jbeg = max(j0, jmin), jend = j0 + kc;
+  if (jbeg >= jend) return;
+  const int steps = 4 * (jend - jbeg);
+  const double* ap[NTL];
+  double2 nxt[NTL];
+  int j = jbeg, c8p = 0;
+#pragma unroll
+  for (int t = 0; t < NTL; ++t) {
+    ap[t] = slab + G.off(j) + (size_t)(TS.rb[t] + r - 32 * j) * 32 + 2 * q;
+    nxt[t] = (j >= TS.js[t]) ? *reinterpret_cast<const double2*>(ap[t]) : make_double2(0.0, 0.0);
+  }
+  for (int st = 0; st < steps; ++st) {
+    double2 av[NTL];
+#pragma unroll
+    for (int t = 0; t < NTL; ++t) av[t] = nxt[t];
+    const int bcol = 32 * (j - j0) + 8 * c8p + 2 * q;
+    if (++c8p == 4) {
+      c8p = 0; ++j;
+#pragma unroll
+      for (int t = 0; t < NTL; ++t) ap[t] = slab + G.off(j) + (size_t)(TS.rb[t] + r - 32 * j) * 32 + 2 * q;
+    } else {
+#pragma unroll
+      for (int t = 0; t < NTL; ++t) ap[t] += 8;
+    }
+    if (st + 1 < steps) {
+#pragma unroll
+      for (int t = 0; t < NTL; ++t)
+        nxt[t] = (j >= TS.js[t]) ? *reinterpret_cast<const double2*>(ap[t]) : make_double2(0.0, 0.0);
+    }
+    double2 bv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      bv[u] = *reinterpret_cast<const double2*>(Bs + (size_t)(8 * u + r) * bstride + bcol);
+#pragma unroll
+    for (int t = 0; t < NTL; ++t) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) dmma(acc[t][u], av[t].x, bv[u].x);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) dmma(acc[t][u], av[t].y, bv[u].y);
+    }
+  }
+}
+
+// C = init - acc;  X = C * L_kk^-T (block forward substitution on DMMA);  store X into panel k.
+template <int NTL>
+__device__ __forceinline__ void finish_tiles(double (&acc)[4][4][2], const TileSet& TS, const CholArgs& A,
+                                             const double* Lt, const double* Wd, double* slab,
+                                             const SlabGeom& G, int k, int n, int npad, int b, int r, int q,
+                                             double& zz) {
+  const int c0 = 32 * k;
+  // Gram values of my tiles for this panel: all loads issued together, branch-free
+  double2 ginit[NTL][4];
+  if (!A.dense) {
+#pragma unroll
+    for (int t = 0; t < NTL; ++t)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int rowc = TS.kind[t] == 0 ? min(TS.rb[t] + r, npad - 1) : c0;
+        ginit[t][u] = *reinterpret_cast<const double2*>(slab + G.off(k) + (size_t)(rowc - c0) * 32 + 8 * u + 2 * q);
+      }
+  }
+#pragma unroll
+  for (int t = 0; t < NTL; ++t) {
+    const int row = TS.rb[t] + r;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int cl = 8 * u + 2 * q, col = c0 + cl;
+      double2 v0 = make_double2(0.0, 0.0);
+      if (TS.kind[t] == 0) {
+        if (A.dense) {
+          if (row < n && col < n) v0.x = A.dense[(size_t)row * A.ldd + col];
+          if (row < n && col + 1 < n) v0.y = A.dense[(size_t)row * A.ldd + col + 1];
+        } else {
+          v0 = ginit[t][u];
+          if (row >= n || col >= n) v0.x = 0.0;
+          if (row >= n || col + 1 >= n) v0.y = 0.0;
         }
-        double v = eval_program(PR, TP, r2[a], same, true);
-        if (same) v += alpha[row];
-        base[(size_t)(row - c0) * 32 + lane] = v;
+      } else if (TS.kind[t] == 1) {
+        if (row == G.Rz && A.y) {
+          if (col < n) v0.x = A.y[col];
+          if (col + 1 < n) v0.y = A.y[col + 1];
+        }
+      } else {
+        v0.x = (row - G.Ra == col) ? 1.0 : 0.0;
+        v0.y = (row - G.Ra == col + 1) ? 1.0 : 0.0;
+      }
+      acc[t][u][0] = v0.x - acc[t][u][0];
+      acc[t][u][1] = v0.y - acc[t][u][1];
+    }
+  }
+  // X_b = (C_b - sum_{a<b} X_a L_ba^T) W_bb^T,  b = 0..3  (8-column blocks)
+#pragma unroll
+  for (int ub = 0; ub < 4; ++ub) {
+#pragma unroll
+    for (int ua = 0; ua < ub; ++ua) {
+      const double2 lv = *reinterpret_cast<const double2*>(Lt + (8 * ub + r) * LS + 8 * ua + 2 * q);
+#pragma unroll
+      for (int t = 0; t < NTL; ++t) {
+        dmma(acc[t][ub], acc[t][ua][0], -lv.x);
+        dmma(acc[t][ub], acc[t][ua][1], -lv.y);
+      }
+    }
+    const double2 wv = *reinterpret_cast<const double2*>(Wd + ub * 64 + r * 8 + 2 * q);
+#pragma unroll
+    for (int t = 0; t < NTL; ++t) {
+      double o[2] = {0.0, 0.0};
+      dmma(o, acc[t][ub][0], wv.x);
+      dmma(o, acc[t][ub][1], wv.y);
+      acc[t][ub][0] = o[0]; acc[t][ub][1] = o[1];
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < NTL; ++t) {
+    const int row = TS.rb[t] + r;
+    double* dst = slab + G.off(k) + (size_t)(row - c0) * 32 + 2 * q;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      *reinterpret_cast<double2*>(dst + 8 * u) = make_double2(acc[t][u][0], acc[t][u][1]);
+    if (TS.kind[t] == 1 && r == 0) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        zz = fma(acc[t][u][0], acc[t][u][0], zz);
+        zz = fma(acc[t][u][1], acc[t][u][1], zz);
+        if (A.z_out) {
+          const int col = c0 + 8 * u + 2 * q;
+          if (col < n) A.z_out[(size_t)b * n + col] = acc[t][u][0];
+          if (col + 1 < n) A.z_out[(size_t)b * n + col + 1] = acc[t][u][1];
+        }
       }
     }
   }
@@ -161,16 +314,12 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
   const int kch = P - 1 < KCH ? (P - 1 > 0 ? P - 1 : 1) : KCH;
   const int bstride = 32 * kch + 8;
   double* Bs = reinterpret_cast<double*>(smem_raw + ((sizeof(CholSmem<NW>) + 15) & ~size_t(15)));  // 32 x bstride
-  // [leaf][dim][npad] scaled training inputs (Gram mode): shared memory when it fits, else a
-  // per-CTA global scratch (same layout, L1/L2 cached)
-  double* Xt = A.xt_scratch ? A.xt_scratch + (size_t)blockIdx.x * A.xt_stride
-                            : Bs + (size_t)32 * bstride;
   if (A.prog) {
     const int* src = reinterpret_cast<const int*>(A.prog);
     int* dst = reinterpret_cast<int*>(&S.prog);
     for (int i = tid; i < (int)(sizeof(DevProgram) / 4); i += NW * 32) dst[i] = src[i];
   } else if (tid == 0) {
-    S.prog.n_ops = 0; S.prog.n_theta = 0; S.prog.n_leaves = 0; S.prog.d = 0;
+    S.prog.n_ops = 0; S.prog.n_theta = 0; S.prog.n_leaves = 0; S.prog.d = 0; S.prog.fast_kind = 0;
   }
   __syncthreads();
   const DevProgram& PR = S.prog;
@@ -178,21 +327,15 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
   for (int b = blockIdx.x; b < A.batch; b += gridDim.x) {
     const double* theta = A.theta + (size_t)b * PR.n_theta;
     double* slab = A.slabs + (size_t)(A.slab_per_block ? blockIdx.x : b) * G.doubles();
-    if (!A.dense) resolve_theta(PR, theta, A.fixed_ls, S.tp, tid, NW * 32);
     if (tid == 0) S.fail = 0;
     double logdet = 0.0, zz = 0.0;   // meaningful in warp 0 / z-row owners
     __syncthreads();
-    if (!A.dense) {
-      for (int e = tid; e < PR.n_leaves * d * npad; e += NW * 32) {
-        const int l = e / (d * npad), rem = e - l * d * npad, kk = rem / npad, i = rem - kk * npad;
-        Xt[e] = (i < n) ? A.X[(size_t)i * d + kk] * S.tp.inv_ls[l][kk] : 0.0;
-      }
-      __syncthreads();
-    }
 
+#define BGP_STAMP(slot) do { if (A.dbg && blockIdx.x == 0 && tid == A.dbg_tid) A.dbg[k * 12 + (slot)] = clock64(); } while (0)
+#define BGP_STAMP_ADD(slot, t0) do { if (A.dbg && blockIdx.x == 0 && tid == A.dbg_tid) A.dbg[k * 12 + (slot)] += clock64() - (t0); } while (0)
     for (int k = 0; k < P; ++k) {
       const int c0 = 32 * k;
-      if (!A.dense) gram_panel<NW>(PR, S.tp, Xt, npad, A.alpha, slab, G, k, n, d, warp, lane);
+      BGP_STAMP(0);
       // ------------------------------------------------ phase 1: diagonal block
       double acc[4][4][2];
 #pragma unroll
@@ -203,13 +346,7 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
       for (int ch = 0; ch < nchunks; ++ch) {
         const int j0 = ch * kch, kc = min(kch, k - j0);
         __syncthreads();
-        // stage rows [c0, c0+32) x columns of panels [j0, j0+kc) of L
-        for (int e = tid; e < 32 * kc * 16; e += NW * 32) {
-          int row = e / (kc * 16), rem = e - row * kc * 16, jj = rem >> 4, c2 = rem & 15;
-          const double2 v = *reinterpret_cast<const double2*>(
-              slab + G.off(j0 + jj) + (size_t)(c0 + row - 32 * (j0 + jj)) * 32 + 2 * c2);
-          *reinterpret_cast<double2*>(Bs + (size_t)row * bstride + 32 * jj + 2 * c2) = v;
-        }
+        stage_block_row(slab, G, Bs, bstride, c0, j0, kc, tid, NW * 32);
         __syncthreads();
         if (warp < 4) {
           for (int c8 = warp; c8 < 4 * kc; c8 += 4) {
@@ -236,7 +373,8 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
             S.Part[warp][(8 * t + r) * PP + 8 * u + 2 * q + 1] = acc[t][u][1];
           }
       }
-      __syncthreads();   // also makes the Gram panel written above visible to the whole CTA
+      __syncthreads();   // also makes the Gram panel (written earlier) visible to the whole CTA
+      BGP_STAMP(1);
       for (int e = tid; e < 1024; e += NW * 32) {
         const int rl = e >> 5, cl = e & 31;
         double v = 0.0;
@@ -254,30 +392,47 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
         S.Dblk[rl * PS + cl] = v;
       }
       __syncthreads();
+      BGP_STAMP(2);
       if (warp == 0) {
-        int f = warp_potrf_inv32(S.Dblk, S.Ws, S.inv_diag, lane, logdet, min(32, n - c0));
+        int f = warp_potrf32(S.Dblk, S.Lt, &S.Wd[0][0], lane, logdet, min(32, n - c0));
         if (f && lane == 0) S.fail = c0 + f;
         // L_kk -> slab (diag group rows of panel k)
-        for (int e = lane; e < 1024; e += 32)
-          slab[G.off(k) + e] = S.Dblk[(e >> 5) * PS + (e & 31)];
+        for (int e = lane; e < 1024; e += 32) slab[G.off(k) + e] = S.Lt[(e >> 5) * LS + (e & 31)];
+        BGP_STAMP(3);
+      } else if (A.dbg && warp == (A.dbg_tid >> 5)) {
+        BGP_STAMP(3);
       }
       __syncthreads();
+      BGP_STAMP(4);
       if (S.fail) break;
 
-      // ------------------------------------------------ phase 2: rows below the block
-      const int n_main = P - 1 - k;
-      const int n_groups = n_main + 1 + (A.aug ? k + 1 : 0);
-      const int rounds = (n_groups + NW - 1) / NW;
+      // ------------------------------------------------ phase 2: rows below the block, 8-row
+      // tiles dealt evenly to the warps (up to four per warp and round)
+      const int n_main_t = 4 * (P - 1 - k);
+      const int n_aug_t = A.aug ? 4 * (k + 1) : 0;
+      const int T = n_main_t + 1 + n_aug_t;
+      // warp w owns the contiguous tiles [w0, w0 + mine); every warp runs the same number of
+      // rounds (barriers inside when K is chunked), each with at most four of its tiles
+      const int tq = T / NW, trm = T % NW;
+      const int mine = tq + (warp < trm ? 1 : 0);
+      const int w0 = warp * tq + min(warp, trm);
+      const int rounds = (tq + (trm ? 1 : 0) + 3) / 4;
+      const int per = rounds ? (mine + rounds - 1) / rounds : 0;
       for (int rd = 0; rd < rounds; ++rd) {
-        const int gi = rd * NW + warp;
-        const bool valid = gi < n_groups;
-        int rb = 0, kind = 0, jstart = 0;   // kind 0 main, 1 z, 2 identity rows
-        if (valid) {
-          if (gi < n_main) { rb = 32 * (k + 1 + gi); kind = 0; }
-          else if (gi == n_main) { rb = G.Rz; kind = 1; }
-          else { int a = gi - n_main - 1; rb = G.Ra + 32 * a; kind = 2; jstart = a; }
+        const int first = w0 + rd * per;
+        const int ntl = max(0, min(w0 + mine, first + per) - first);   // tiles of this warp and round
+        TileSet TS;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int ti = first + t;
+          TS.rb[t] = c0; TS.kind[t] = 3; TS.js[t] = 0;   // kind 3: padding slot of the tile set
+          if (t < ntl) {
+            if (ti < n_main_t) { TS.rb[t] = 32 * (k + 1) + 8 * ti; TS.kind[t] = 0; }
+            else if (ti == n_main_t) { TS.rb[t] = G.Rz; TS.kind[t] = 1; }
+            else { const int a = ti - n_main_t - 1; TS.rb[t] = G.Ra + 8 * a; TS.kind[t] = 2; TS.js[t] = a >> 2; }
+          }
         }
-        const int mt = (kind == 1) ? 1 : 4;
+        long long tph = clock64();
 #pragma unroll
         for (int t = 0; t < 4; ++t)
 #pragma unroll
@@ -286,141 +441,33 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
           const int j0 = ch * kch, kc = min(kch, k - j0);
           if (nchunks > 1) {
             __syncthreads();
-            for (int e = tid; e < 32 * kc * 16; e += NW * 32) {
-              int row = e / (kc * 16), rem = e - row * kc * 16, jj = rem >> 4, c2 = rem & 15;
-              const double2 v = *reinterpret_cast<const double2*>(
-                  slab + G.off(j0 + jj) + (size_t)(c0 + row - 32 * (j0 + jj)) * 32 + 2 * c2);
-              *reinterpret_cast<double2*>(Bs + (size_t)row * bstride + 32 * jj + 2 * c2) = v;
-            }
+            stage_block_row(slab, G, Bs, bstride, c0, j0, kc, tid, NW * 32);
             __syncthreads();
           }
-          if (!valid) continue;
-          const int jbeg = max(j0, jstart), jend = j0 + kc;
-          if (jbeg >= jend) continue;
-          // stream A (my 32 rows of the previous panels) from the slab, one 8-column step ahead
-          const int steps = 4 * (jend - jbeg);
-          const double* ap[4];
-          double2 nxt[4];
-          int j = jbeg, c8p = 0;
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            ap[t] = slab + G.off(j) + (size_t)(rb + 8 * t + r - 32 * j) * 32 + 2 * q;
-            nxt[t] = (t < mt) ? *reinterpret_cast<const double2*>(ap[t]) : make_double2(0, 0);
-          }
-          for (int st = 0; st < steps; ++st) {
-            double2 av[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) av[t] = nxt[t];
-            const int bcol = 32 * (j - j0) + 8 * c8p + 2 * q;
-            // advance + prefetch
-            if (++c8p == 4) {
-              c8p = 0; ++j;
-#pragma unroll
-              for (int t = 0; t < 4; ++t)
-                ap[t] = slab + G.off(j) + (size_t)(rb + 8 * t + r - 32 * j) * 32 + 2 * q;
-            } else {
-#pragma unroll
-              for (int t = 0; t < 4; ++t) ap[t] += 8;
-            }
-            if (st + 1 < steps) {
-#pragma unroll
-              for (int t = 0; t < 4; ++t)
-                if (t < mt) nxt[t] = *reinterpret_cast<const double2*>(ap[t]);
-            }
-            double2 bv[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              bv[u] = *reinterpret_cast<const double2*>(Bs + (size_t)(8 * u + r) * bstride + bcol);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              if (t < mt) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  dmma(acc[t][u], av[t].x, bv[u].x);
-                  dmma(acc[t][u], av[t].y, bv[u].y);
-                }
-              }
-            }
+          switch (ntl) {
+            case 4: k_chunk<4>(acc, TS, slab, G, Bs, bstride, j0, kc, r, q); break;
+            case 3: k_chunk<3>(acc, TS, slab, G, Bs, bstride, j0, kc, r, q); break;
+            case 2: k_chunk<2>(acc, TS, slab, G, Bs, bstride, j0, kc, r, q); break;
+            case 1: k_chunk<1>(acc, TS, slab, G, Bs, bstride, j0, kc, r, q); break;
+            default: break;
           }
         }
-        if (!valid) continue;
-        // C = init - acc, in accumulator layout (init: Gram panel in the slab / y / identity)
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          if (t >= mt) continue;
-          const int row = rb + 8 * t + r;
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int cl = 8 * u + 2 * q, col = c0 + cl;
-            double2 v0 = make_double2(0.0, 0.0);
-            if (kind == 0) {
-              if (row < n) {
-                if (A.dense) {
-                  if (col < n) v0.x = A.dense[(size_t)row * A.ldd + col];
-                  if (col + 1 < n) v0.y = A.dense[(size_t)row * A.ldd + col + 1];
-                } else {
-                  v0 = *reinterpret_cast<const double2*>(slab + G.off(k) + (size_t)(row - c0) * 32 + cl);
-                  if (col >= n) v0.x = 0.0;
-                  if (col + 1 >= n) v0.y = 0.0;
-                }
-              }
-            } else if (kind == 1) {
-              if (row == G.Rz && A.y) {
-                if (col < n) v0.x = A.y[col];
-                if (col + 1 < n) v0.y = A.y[col + 1];
-              }
-            } else {
-              v0.x = (row - G.Ra == col) ? 1.0 : 0.0;
-              v0.y = (row - G.Ra == col + 1) ? 1.0 : 0.0;
-            }
-            acc[t][u][0] = v0.x - acc[t][u][0];
-            acc[t][u][1] = v0.y - acc[t][u][1];
-          }
+        BGP_STAMP_ADD(7, tph); tph = clock64();
+        double zpart = 0.0;
+        switch (ntl) {
+          case 4: finish_tiles<4>(acc, TS, A, S.Lt, &S.Wd[0][0], slab, G, k, n, npad, b, r, q, zpart); break;
+          case 3: finish_tiles<3>(acc, TS, A, S.Lt, &S.Wd[0][0], slab, G, k, n, npad, b, r, q, zpart); break;
+          case 2: finish_tiles<2>(acc, TS, A, S.Lt, &S.Wd[0][0], slab, G, k, n, npad, b, r, q, zpart); break;
+          case 1: finish_tiles<1>(acc, TS, A, S.Lt, &S.Wd[0][0], slab, G, k, n, npad, b, r, q, zpart); break;
+          default: break;
         }
-        // X = C * W^T through DMMA, in place (descending output tile)
-#pragma unroll
-        for (int uo = 3; uo >= 0; --uo) {
-          double o[4][2];
-#pragma unroll
-          for (int t = 0; t < 4; ++t) o[t][0] = o[t][1] = 0.0;
-#pragma unroll
-          for (int ui = 0; ui <= uo; ++ui) {
-            const double2 wv = *reinterpret_cast<const double2*>(S.Ws + (8 * uo + r) * WS + 8 * ui + 2 * q);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              if (t < mt) {
-                dmma(o[t], acc[t][ui][0], wv.x);
-                dmma(o[t], acc[t][ui][1], wv.y);
-              }
-            }
-          }
-#pragma unroll
-          for (int t = 0; t < 4; ++t) { acc[t][uo][0] = o[t][0]; acc[t][uo][1] = o[t][1]; }
-        }
-        // store the finished rows of panel k
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          if (t >= mt) continue;
-          const int row = rb + 8 * t + r;
-          double* dst = slab + G.off(k) + (size_t)(row - c0) * 32 + 2 * q;
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            *reinterpret_cast<double2*>(dst + 8 * u) = make_double2(acc[t][u][0], acc[t][u][1]);
-        }
-        if (kind == 1 && r == 0) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            zz = fma(acc[0][u][0], acc[0][u][0], zz);
-            zz = fma(acc[0][u][1], acc[0][u][1], zz);
-            if (A.z_out) {
-              int col = c0 + 8 * u + 2 * q;
-              if (col < n) A.z_out[(size_t)b * n + col] = acc[0][u][0];
-              if (col + 1 < n) A.z_out[(size_t)b * n + col + 1] = acc[0][u][1];
-            }
-          }
-        }
+        zz += zpart;
+        BGP_STAMP_ADD(8, tph);
       }
+      BGP_STAMP(5);
       __syncthreads();
+      BGP_STAMP(6);
+      (void)0;
     }
 
     // ------------------------------------------------------------------ epilogue
@@ -449,43 +496,29 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
   }
 }
 
-static int pick_nw(int n) { return n <= 64 ? 4 : 16; }
+static int pick_nw(int n) { return n <= 64 ? 4 : 8; }
 
-static size_t smem_base(int n) {
+static size_t chol_smem_bytes(int n) {
   const int P = (n + 31) / 32;
   const int kch = P - 1 < KCH ? (P - 1 > 0 ? P - 1 : 1) : KCH;
-  size_t base = pick_nw(n) == 16 ? sizeof(CholSmem<16>) : sizeof(CholSmem<4>);
+  size_t base = pick_nw(n) == 8 ? sizeof(CholSmem<8>) : sizeof(CholSmem<4>);
   base = (base + 15) & ~size_t(15);
   return base + sizeof(double) * (size_t)32 * (32 * kch + 8);
 }
 
-// doubles of per-CTA global scratch the scaled inputs need when they do not fit in shared memory
-size_t chol_xt_doubles(int n, int d, int n_leaves) {
-  return (size_t)(n_leaves > 0 ? n_leaves : 1) * d * (32 * ((n + 31) / 32));
-}
-size_t chol_xt_scratch_doubles(int n, int d, int n_leaves) {
-  const size_t xt = chol_xt_doubles(n, d, n_leaves);
-  return smem_base(n) + sizeof(double) * xt <= 226 * 1024 ? 0 : xt;
-}
-
-static size_t chol_smem_bytes(int n, int d, int n_leaves, bool dense) {
-  if (dense || chol_xt_scratch_doubles(n, d, n_leaves)) return smem_base(n);
-  return smem_base(n) + sizeof(double) * chol_xt_doubles(n, d, n_leaves);
-}
-
 // opt-in to the large dynamic shared-memory carve-out (must happen outside stream capture)
-cudaError_t prepare_chol(int n, int d, int n_leaves, bool dense) {
-  const size_t smem = chol_smem_bytes(n, d, n_leaves, dense);
+cudaError_t prepare_chol(int n) {
+  const size_t smem = chol_smem_bytes(n);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   return pick_nw(n) == 4
              ? cudaFuncSetAttribute(chol_lml_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-             : cudaFuncSetAttribute(chol_lml_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+             : cudaFuncSetAttribute(chol_lml_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
-cudaError_t launch_chol(const CholArgs& A, int grid, int n_leaves, cudaStream_t stream) {
-  const size_t smem = chol_smem_bytes(A.n, A.d, n_leaves, A.dense != nullptr);
+cudaError_t launch_chol(const CholArgs& A, int grid, cudaStream_t stream) {
+  const size_t smem = chol_smem_bytes(A.n);
   if (pick_nw(A.n) == 4) chol_lml_kernel<4><<<grid, 128, smem, stream>>>(A);
-  else chol_lml_kernel<16><<<grid, 512, smem, stream>>>(A);
+  else chol_lml_kernel<8><<<grid, 256, smem, stream>>>(A);
   return cudaGetLastError();
 }
 

@@ -38,6 +38,9 @@ struct SlabGeom {
 // ------------------------------------------------------------------- covariance program
 struct DevProgram {
   int n_ops, n_theta, n_leaves, d;
+  // fast path for the shape  c * stationary(r) + white  (the default bask kernel): opcode of the
+  // stationary leaf (0 = use the interpreter) and the op slots of the constant / white levels
+  int fast_kind, fast_const, fast_white, fast_white_zeroable;
   bgp_op_t ops[BGP_MAX_OPS];
   int leaf_of_op[BGP_MAX_OPS];
 };
@@ -83,8 +86,26 @@ __device__ __forceinline__ double pick_leaf(const double* r2, int leaf) {
   return v;
 }
 
+__device__ __forceinline__ double stationary_value(int code, double r2) {
+  if (code == BGP_OP_MATERN52) {
+    const double t = sqrt(r2) * 2.23606797749979;
+    return (1.0 + t + t * t * 0.3333333333333333) * exp(-t);
+  }
+  if (code == BGP_OP_RBF) return exp(-0.5 * r2);
+  if (code == BGP_OP_MATERN32) {
+    const double t = sqrt(r2) * 1.7320508075688772;
+    return (1.0 + t) * exp(-t);
+  }
+  return exp(-sqrt(r2));
+}
+
 __device__ __forceinline__ double eval_program(const DevProgram& P, const ThetaParams& T,
                                                const double* r2, bool same_point, bool white_on) {
+  if (P.fast_kind) {
+    double v = T.opval[P.fast_const] * stationary_value(P.fast_kind, r2[0]);
+    if (same_point && (white_on || !P.fast_white_zeroable)) v += T.opval[P.fast_white];
+    return v;
+  }
   double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
 #define BGP_PUSH(v) { s3 = s2; s2 = s1; s1 = s0; s0 = (v); }
 #define BGP_BIN(expr) { double _a = s1, _b = s0; s0 = (expr); s1 = s2; s2 = s3; }

@@ -1,0 +1,125 @@
+// K1: batched-theta kernel-matrix construction.  One launch builds the lower triangle of
+// K_theta(X, X) + diag(alpha) for every theta of the batch, panel by panel, directly in the
+// tiled factor-slab layout the factorisation kernel consumes (so the matrix lives in L2 between
+// the two kernels and is never read from HBM as an input).  ARD scaled differences use the
+// difference form (no ||a||^2 + ||b||^2 - 2ab cancellation); the diagonal is exact.
+// Replaces kernel(self.X_train_) of sklearn:_gpr.py:586 / bask/bayesgpr.py:203.
+//
+// Why a separate kernel: with W/2 = 64 thetas per MCMC half step only 64 of the 148 SMs run a
+// factorisation; the Gram build is embarrassingly parallel FP64 ALU work (sqrt + exp per entry)
+// and spreads over all SMs here instead of stretching each factorisation CTA's critical path.
+#include "bgp_common.cuh"
+#include "bgp_internal.h"
+
+namespace bgp {
+
+// Xt[b][leaf][dim][npad] = X[i][dim] / length_scale(theta_b, leaf, dim), zero padded
+__global__ void __launch_bounds__(256) scale_x_kernel(GramArgs A) {
+  __shared__ DevProgram PR;
+  __shared__ ThetaParams TP;
+  const int tid = threadIdx.x, b = blockIdx.y;
+  {
+    const int* src = reinterpret_cast<const int*>(A.prog);
+    int* dst = reinterpret_cast<int*>(&PR);
+    for (int i = tid; i < (int)(sizeof(DevProgram) / 4); i += 256) dst[i] = src[i];
+  }
+  __syncthreads();
+  resolve_theta(PR, A.theta + (size_t)b * PR.n_theta, A.fixed_ls, TP, tid, 256);
+  __syncthreads();
+  const int npad = 32 * ((A.n + 31) / 32), d = A.d;
+  double* Xt = A.xt + (size_t)b * A.xt_stride;
+  for (int e = blockIdx.x * 256 + tid; e < PR.n_leaves * d * npad; e += gridDim.x * 256) {
+    const int l = e / (d * npad), rem = e - l * d * npad, kk = rem / npad, i = rem - kk * npad;
+    Xt[e] = (i < A.n) ? A.X[(size_t)i * d + kk] * TP.inv_ls[l][kk] : 0.0;
+  }
+}
+
+// CTA (panel k, theta b): rows [32k, n) x 32 columns of the lower triangle.  A warp takes
+// eight rows per iteration (eight independent sqrt/exp chains), lanes are the 32 columns.
+__global__ void __launch_bounds__(256) gram_kernel(GramArgs A) {
+  __shared__ DevProgram PR;
+  __shared__ ThetaParams TP;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.y, k = blockIdx.x, n = A.n, d = A.d;
+  {
+    const int* src = reinterpret_cast<const int*>(A.prog);
+    int* dst = reinterpret_cast<int*>(&PR);
+    for (int i = tid; i < (int)(sizeof(DevProgram) / 4); i += 256) dst[i] = src[i];
+  }
+  __syncthreads();
+  resolve_theta(PR, A.theta + (size_t)b * PR.n_theta, A.fixed_ls, TP, tid, 256);
+  __syncthreads();
+  const SlabGeom G = SlabGeom::make(n, A.aug != 0);
+  const int npad = 32 * G.P;
+  const double* Xt = A.xt + (size_t)b * A.xt_stride;
+  double* base = A.slabs + (size_t)b * G.doubles() + G.off(k);
+  constexpr int RB = 8;
+  const int c0 = 32 * k, col = c0 + lane;
+  for (int r0 = c0 + RB * warp; r0 < n; r0 += RB * 8) {
+    if (PR.fast_kind) {
+      double r2[RB];
+#pragma unroll
+      for (int a = 0; a < RB; ++a) r2[a] = 0.0;
+      for (int kk = 0; kk < d; ++kk) {
+        const double* xr = Xt + (size_t)kk * npad;
+        const double xc = xr[col];
+#pragma unroll
+        for (int a = 0; a < RB; ++a) {
+          const double t = xr[min(r0 + a, npad - 1)] - xc;
+          r2[a] = fma(t, t, r2[a]);
+        }
+      }
+      const double cval = TP.opval[PR.fast_const], wval = TP.opval[PR.fast_white];
+      double v[RB];
+#pragma unroll
+      for (int a = 0; a < RB; ++a) {
+        const bool same = (r0 + a) == col;
+        v[a] = cval * stationary_value(PR.fast_kind, same ? 0.0 : r2[a]);
+        if (same) v[a] += wval + A.alpha[min(r0 + a, n - 1)];
+      }
+#pragma unroll
+      for (int a = 0; a < RB; ++a) {
+        const int row = r0 + a;
+        if (row < n && col <= row) base[(size_t)(row - c0) * 32 + lane] = v[a];
+      }
+    } else {
+      for (int a = 0; a < RB; ++a) {
+        const int row = r0 + a;
+        if (row >= n || col > row) continue;
+        double r2[BGP_MAX_LEAVES];
+#pragma unroll
+        for (int l = 0; l < BGP_MAX_LEAVES; ++l) {
+          r2[l] = 0.0;
+          if (l < PR.n_leaves && row != col) {
+            const double* xl = Xt + (size_t)l * d * npad;
+            double acc2 = 0.0;
+            for (int kk = 0; kk < d; ++kk) {
+              const double t = xl[(size_t)kk * npad + row] - xl[(size_t)kk * npad + col];
+              acc2 = fma(t, t, acc2);
+            }
+            r2[l] = acc2;
+          }
+        }
+        double v = eval_program(PR, TP, r2, row == col, true);
+        if (row == col) v += A.alpha[row];
+        base[(size_t)(row - c0) * 32 + lane] = v;
+      }
+    }
+  }
+}
+
+size_t gram_xt_doubles(int n, int d, int n_leaves) {
+  return (size_t)(n_leaves > 0 ? n_leaves : 1) * d * (32 * ((n + 31) / 32));
+}
+
+cudaError_t launch_gram(const GramArgs& A, cudaStream_t stream) {
+  const int P = (A.n + 31) / 32;
+  const int per_theta = (int)((gram_xt_doubles(A.n, A.d, 1) * 4 + 255) / 256);
+  dim3 gs(per_theta < 1 ? 1 : (per_theta > 32 ? 32 : per_theta), A.batch);
+  scale_x_kernel<<<gs, 256, 0, stream>>>(A);
+  dim3 gg(P, A.batch);
+  gram_kernel<<<gg, 256, 0, stream>>>(A);
+  return cudaGetLastError();
+}
+
+}  // namespace bgp

@@ -28,12 +28,25 @@ struct CholArgs {
   const double* dense;   // when set: factor this dense SPD matrix (lower part read) instead of a Gram
   long long ldd;
   double jitter;
-  double* xt_scratch;    // per-CTA scratch for the scaled inputs when they do not fit in shared memory
-  long long xt_stride;
+  long long* dbg;        // optional clock64 stamps of CTA 0 (12 per panel), developer tooling
+  int dbg_tid;           // thread that records them
 };
-cudaError_t prepare_chol(int n, int d, int n_leaves, bool dense);
-size_t chol_xt_scratch_doubles(int n, int d, int n_leaves);
-cudaError_t launch_chol(const CholArgs& A, int grid, int n_leaves, cudaStream_t stream);
+cudaError_t prepare_chol(int n);
+cudaError_t launch_chol(const CholArgs& A, int grid, cudaStream_t stream);
+
+struct GramArgs {
+  const double* X;       // n x d
+  const double* alpha;   // n
+  const double* theta;   // batch x p
+  double* slabs;         // batch factor slabs (the lower triangle of each is written)
+  double* xt;            // scratch: batch x xt_stride scaled, transposed inputs
+  long long xt_stride;
+  const DevProgram* prog;
+  const double* fixed_ls;
+  int n, d, batch, aug;
+};
+size_t gram_xt_doubles(int n, int d, int n_leaves);
+cudaError_t launch_gram(const GramArgs& A, cudaStream_t stream);
 
 struct SweepArgs {
   const double* X;        // n x d
