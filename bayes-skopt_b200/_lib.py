@@ -44,6 +44,11 @@ _SIGNATURES = {
                             _P, _P, _P, C.c_int, _P, _P, C.c_int64, _P],
     "bgp_acq_sweep": [_P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_double, _P, C.c_int, _P, _P, _P, _P, _P],
     "bgp_argmax": [_P, _P, C.c_int, _P, _P],
+    "bgp_acq_stats": [_P, _P, _P, C.c_int, C.c_int, _P, _P],
+    "bgp_mes_fit": [_P, _P, _P, C.c_int, C.c_int, _P, _P],
+    "bgp_ei_best": [_P, _P, _P, C.c_int, C.c_int, C.c_double, _P, C.c_int64, _P, _P],
+    "bgp_acq_per_theta": [_P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_double, _P, _P, _P, C.c_int, _P, _P, _P, _P],
+    "bgp_acq_combine": [_P, _P, C.c_int, C.c_int, _P, _P, _P],
     "bgp_mcmc_run": [_P, _P, _P, C.c_int, C.c_int, C.c_double, C.c_uint64, _P, _P, _P, _P],
     "bgp_mcmc_split": [_P, C.c_int, C.c_uint64, C.c_int, _P, _P],
     "bgp_mcmc_propose": [_P, _P, _P, C.c_int, C.c_int, C.c_double, C.c_uint64, C.c_int, _P, _P, _P, _P],

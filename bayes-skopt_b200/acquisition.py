@@ -190,10 +190,15 @@ class PVRS(FullGPAcquisition):
 
 
 def evaluate_acquisitions(X, gpr, acquisition_functions=None, n_samples=10, progress=False,
-                          random_state=None, **kwargs):
+                          random_state=None, process_group=None, **kwargs):
     """Evaluates acquisition functions on candidate points, averaged over ``n_samples`` draws
     from the hyper-posterior chain.  Same arguments, RNG consumption and output as
-    bask/acquisition.py:48-147; returns ``(len(acquisition_functions), len(X))`` float64."""
+    bask/acquisition.py:48-147; returns ``(len(acquisition_functions), len(X))`` float64.
+
+    ``process_group`` (additive): a torch.distributed group with one rank per GPU.  Every rank
+    passes identical arguments; the built-in (mu, std) acquisitions are then swept over
+    candidates sharded across the ranks (bask_b200/distributed.py) and every rank receives the
+    full result.  Full-GP and sample acquisitions are computed redundantly (replicas only)."""
     X = np.asarray(X, dtype=np.float64)
     n_cand_points = len(X)
     n_acqs = len(acquisition_functions)
@@ -211,11 +216,17 @@ def evaluate_acquisitions(X, gpr, acquisition_functions=None, n_samples=10, prog
     has_smp = any(isinstance(a, SampleAcquisition) for a in acquisition_functions)
     if S == 0 or not (has_unc or has_smp):
         return acq_output
+    sharded = process_group is not None and torch.distributed.get_world_size(process_group) > 1
     Xd = e.to_dev(X)
     y_mean = float(np.atleast_1d(gpr.y_train_mean_)[0])
     y_std = float(np.atleast_1d(gpr.y_train_std_)[0])
     mu = sd = None
-    if has_unc:
+    all_builtin = all(type(a).__call__ is _DeviceUncertainty.__call__ for a in acquisition_functions
+                      if isinstance(a, UncertaintyAcquisition))
+    if sharded and not all_builtin:
+        raise NotImplementedError("user-defined UncertaintyAcquisition classes are not supported with a "
+                                  "process_group (they need the moments of all candidates on one rank)")
+    if has_unc and not sharded:
         th = e.to_dev(gpr.chain_[trace_sample_i])
         f = e.factorize(th)
         info = e.to_host(f.info)
@@ -247,7 +258,17 @@ def evaluate_acquisitions(X, gpr, acquisition_functions=None, n_samples=10, prog
         out, _ = gpr._joint_draws_dev(Xd, th_s, f_s, eps, noise=False)
         samples = e.to_host(out)[:, :, 0]                       # (S, m)
     mu_h = sd_h = None
+    if sharded and has_unc:
+        from .distributed import DeviceBackend, ShardedSweep
+        idx = [j for j, a in enumerate(acquisition_functions) if isinstance(a, _DeviceUncertainty)]
+        spec = [(acquisition_functions[j].kind, acquisition_functions[j]._params(kwargs)[0]) for j in idx]
+        gmb = {i: np.stack(gumbels[j]) for i, j in enumerate(idx) if j in gumbels}
+        vals = ShardedSweep(DeviceBackend(gpr), process_group).evaluate(X, gpr.chain_[trace_sample_i], spec, gmb)
+        for i, j in enumerate(idx):
+            acq_output[j] += vals[i]
     for j, acq in enumerate(acquisition_functions):
+        if sharded and isinstance(acq, UncertaintyAcquisition):
+            continue
         if isinstance(acq, _DeviceUncertainty) and type(acq).__call__ is _DeviceUncertainty.__call__:
             g = np.stack(gumbels[j]) if j in gumbels else None
             out, _per, _skipped, _ = acq.device_eval(e, mu, sd, kwargs, gumbel=g)

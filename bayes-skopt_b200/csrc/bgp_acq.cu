@@ -9,7 +9,7 @@
 namespace bgp {
 
 constexpr int MES_PTS = 192;      // trial points evaluated per refinement round (3 x 64)
-constexpr int MES_CH = 2048;      // candidates per block in the quantile search
+constexpr int MES_CH = 512;       // candidates per block in the quantile search
 constexpr int MES_NEWTON = 10;
 constexpr int ST = 8;             // doubles of per-theta statistics
 constexpr int MS = 16;            // doubles of per-theta MES search state
@@ -101,11 +101,13 @@ __global__ void acq_stats_kernel(const double* __restrict__ mu, const double* __
   }
 }
 
+// y_opt: explicit scalar (y_opt_in not NaN), else per-theta array yopt (stride ystride doubles)
 __global__ void ei_kernel(const double* __restrict__ mu, const double* __restrict__ sd, int m,
-                          const double* __restrict__ stats, double y_opt_in, double* __restrict__ out) {
+                          const double* __restrict__ yopt, int ystride, double y_opt_in,
+                          double* __restrict__ out) {
   const int s = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
-  const double y_opt = isnan(y_opt_in) ? stats[s * ST + 0] : y_opt_in;
+  const double y_opt = isnan(y_opt_in) ? yopt[s * ystride] : y_opt_in;
   const double a = mu[(size_t)s * m + i], b = sd[(size_t)s * m + i];
   out[(size_t)s * m + i] = (b > 0.0) ? ei_f((y_opt - a) / b) * b : 0.0;
 }
@@ -124,13 +126,24 @@ __global__ void argmax_rows_kernel(const double* __restrict__ v, int m, long lon
   if (threadIdx.x == 0) idx[s] = bi;
 }
 
+// ref[s] = {ei max, global index, mu, sd} of the EI-maximising candidate of theta s
+__global__ void ttei_ref_kernel(const double* __restrict__ mu, const double* __restrict__ sd,
+                                const double* __restrict__ ei, int m, const long long* __restrict__ imax,
+                                long long index_offset, double* __restrict__ ref) {
+  const int s = threadIdx.x;
+  const long long j = imax[s];
+  ref[s * 4 + 0] = ei[(size_t)s * m + j];
+  ref[s * 4 + 1] = (double)(j + index_offset);
+  ref[s * 4 + 2] = mu[(size_t)s * m + j];
+  ref[s * 4 + 3] = sd[(size_t)s * m + j];
+}
+
 __global__ void ttei_kernel(const double* __restrict__ mu, const double* __restrict__ sd, int m,
-                            const long long* __restrict__ imax, double* __restrict__ out) {
+                            const double* __restrict__ ref, double* __restrict__ out) {
   const int s = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
-  const long long j = imax[s];
   const double a = mu[(size_t)s * m + i], b = sd[(size_t)s * m + i];
-  const double aj = mu[(size_t)s * m + j], bj = sd[(size_t)s * m + j];
+  const double aj = ref[s * 4 + 2], bj = ref[s * 4 + 3];
   double v = 0.0;
   if (b > 0.0) {
     const double outer = sqrt(b * b + bj * bj);
@@ -255,11 +268,11 @@ __global__ void mes_control_kernel(int phase, int nblk, double* __restrict__ pts
 
 // mean_k [ gamma phi(gamma) / (2 Phi(gamma)) - log Phi(gamma) ],  gamma = (maxv_k + mu)/sd
 __global__ void mes_epilogue_kernel(const double* __restrict__ mu, const double* __restrict__ sd, int m,
-                                    const float* __restrict__ gumbel, int K, const double* __restrict__ st,
+                                    const float* __restrict__ gumbel, int K, const double* __restrict__ fit,
                                     double* __restrict__ out) {
   extern __shared__ double maxv[];
   const int s = blockIdx.y;
-  const double alpha = st[s * MS + 9], beta = st[s * MS + 10];
+  const double alpha = fit[s * 5 + 0], beta = fit[s * 5 + 1];
   for (int k = threadIdx.x; k < K; k += blockDim.x)
     maxv[k] = (double)gumbel[(size_t)s * K + k] * beta + alpha;
   __syncthreads();
@@ -310,30 +323,78 @@ __global__ void combine_kernel(const double* __restrict__ v, int S, int m, const
 
 size_t acq_scratch_doubles(int S, int m) {
   const size_t nblk = (m + MES_CH - 1) / MES_CH;
-  return (size_t)S * (ST + MS + MES_PTS + 8) + 2 * (size_t)S * nblk * MES_PTS + (size_t)S * m + 64;
+  return (size_t)S * (ST + MS + MES_PTS + 8 + 5 + 4) + 2 * (size_t)S * nblk * MES_PTS + (size_t)S * m + 64;
 }
 
-cudaError_t launch_acq(const AcqArgs& A, cudaStream_t stream) {
-  const int S = A.S, m = A.m;
-  if (S <= 0) return cudaSuccess;
+struct AcqScratch {
+  double *stats, *st, *pts, *fit, *ref, *gpart, *dpart, *tmp;
+  long long* imax;
+};
+static AcqScratch carve(double* base, int S, int m) {
+  const size_t nblk = (m + MES_CH - 1) / MES_CH;
+  AcqScratch w;
+  w.stats = base;
+  w.st = w.stats + (size_t)S * ST;
+  w.pts = w.st + (size_t)S * MS;
+  w.imax = reinterpret_cast<long long*>(w.pts + (size_t)S * MES_PTS);
+  w.fit = w.pts + (size_t)S * MES_PTS + (size_t)S * 8;
+  w.ref = w.fit + (size_t)S * 5;
+  w.gpart = w.ref + (size_t)S * 4;
+  w.dpart = w.gpart + (size_t)S * nblk * MES_PTS;
+  w.tmp = w.dpart + (size_t)S * nblk * MES_PTS;
+  return w;
+}
+
+// stats_out (S x 4): min mu, min(-mu - 3 sd), max(-mu + 5 sd), all-finite flag
+cudaError_t launch_acq_stats(const double* mu, const double* sd, int S, int m, double* stats_out,
+                             double* scratch, cudaStream_t stream) {
+  AcqScratch w = carve(scratch, S, m);
+  acq_stats_kernel<<<S, 1024, 0, stream>>>(mu, sd, m, w.stats, w.pts);
+  if (stats_out) cudaMemcpy2DAsync(stats_out, 4 * sizeof(double), w.stats, ST * sizeof(double), 4 * sizeof(double), S,
+                                   cudaMemcpyDeviceToDevice, stream);
+  return cudaGetLastError();
+}
+
+// Gumbel fit of the max-value distribution (needs a preceding launch_acq_stats on the same data)
+cudaError_t launch_mes_fit(const double* mu, const double* sd, int S, int m, double* fit_out, double* scratch,
+                           cudaStream_t stream) {
+  AcqScratch w = carve(scratch, S, m);
   const int nblk = (m + MES_CH - 1) / MES_CH;
-  double* stats = A.scratch;
-  double* st = stats + (size_t)S * ST;
-  double* pts = st + (size_t)S * MS;
-  long long* imax = reinterpret_cast<long long*>(pts + (size_t)S * MES_PTS);
-  double* gpart = pts + (size_t)S * MES_PTS + (size_t)S * 8;
-  double* dpart = gpart + (size_t)S * nblk * MES_PTS;
-  double* tmp = dpart + (size_t)S * nblk * MES_PTS;   // S x m
+  dim3 gq(nblk, S);
+  mes_eval_kernel<<<gq, 256, 0, stream>>>(mu, sd, m, w.pts, 64, 0, w.gpart, w.dpart);
+  mes_control_kernel<<<S, 32, 0, stream>>>(1, nblk, w.pts, w.gpart, w.dpart, w.st, nullptr);
+  mes_eval_kernel<<<gq, 256, 0, stream>>>(mu, sd, m, w.pts, MES_PTS, 0, w.gpart, w.dpart);
+  mes_control_kernel<<<S, 32, 0, stream>>>(2, nblk, w.pts, w.gpart, w.dpart, w.st, nullptr);
+  for (int it = 0; it < MES_NEWTON; ++it) {
+    mes_eval_kernel<<<gq, 256, 0, stream>>>(mu, sd, m, w.pts, 3, 1, w.gpart, w.dpart);
+    mes_control_kernel<<<S, 32, 0, stream>>>(3, nblk, w.pts, w.gpart, w.dpart, w.st, nullptr);
+  }
+  mes_control_kernel<<<S, 32, 0, stream>>>(4, nblk, w.pts, w.gpart, w.dpart, w.st, fit_out ? fit_out : w.fit);
+  return cudaGetLastError();
+}
+
+// local EI maximiser per theta: ref_out (S x 4) = {ei max, global index, mu, sd}
+cudaError_t launch_ei_best(const double* mu, const double* sd, int S, int m, double p0, const double* yopt,
+                           long long index_offset, double* ref_out, double* scratch, cudaStream_t stream) {
+  if (S > 1024) return cudaErrorInvalidValue;
+  AcqScratch w = carve(scratch, S, m);
   dim3 ge((m + 255) / 256, S);
-  acq_stats_kernel<<<S, 1024, 0, stream>>>(A.mu, A.sd, m, stats, A.kind == BGP_ACQ_MES ? pts : nullptr);
+  ei_kernel<<<ge, 256, 0, stream>>>(mu, sd, m, yopt ? yopt : w.stats, yopt ? 1 : ST, p0, w.tmp);
+  argmax_rows_kernel<<<S, 1024, 0, stream>>>(w.tmp, m, w.imax);
+  ttei_ref_kernel<<<1, S, 0, stream>>>(mu, sd, w.tmp, m, w.imax, index_offset, ref_out ? ref_out : w.ref);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_acq_per_theta(const AcqArgs& A, cudaStream_t stream) {
+  const int S = A.S, m = A.m;
+  AcqScratch w = carve(A.scratch, S, m);
+  dim3 ge((m + 255) / 256, S);
   switch (A.kind) {
     case BGP_ACQ_EI:
-      ei_kernel<<<ge, 256, 0, stream>>>(A.mu, A.sd, m, stats, A.p0, A.per_theta);
+      ei_kernel<<<ge, 256, 0, stream>>>(A.mu, A.sd, m, A.yopt ? A.yopt : w.stats, A.yopt ? 1 : ST, A.p0, A.per_theta);
       break;
     case BGP_ACQ_TTEI:
-      ei_kernel<<<ge, 256, 0, stream>>>(A.mu, A.sd, m, stats, A.p0, tmp);
-      argmax_rows_kernel<<<S, 1024, 0, stream>>>(tmp, m, imax);
-      ttei_kernel<<<ge, 256, 0, stream>>>(A.mu, A.sd, m, imax, A.per_theta);
+      ttei_kernel<<<ge, 256, 0, stream>>>(A.mu, A.sd, m, A.ref ? A.ref : w.ref, A.per_theta);
       break;
     case BGP_ACQ_MEAN:
     case BGP_ACQ_LCB:
@@ -341,24 +402,39 @@ cudaError_t launch_acq(const AcqArgs& A, cudaStream_t stream) {
       break;
     case BGP_ACQ_MES: {
       if (!A.u32 || A.K <= 0) return cudaErrorInvalidValue;
-      dim3 gq(nblk, S);
-      mes_eval_kernel<<<gq, 256, 0, stream>>>(A.mu, A.sd, m, pts, 64, 0, gpart, dpart);
-      mes_control_kernel<<<S, 32, 0, stream>>>(1, nblk, pts, gpart, dpart, st, nullptr);
-      mes_eval_kernel<<<gq, 256, 0, stream>>>(A.mu, A.sd, m, pts, MES_PTS, 0, gpart, dpart);
-      mes_control_kernel<<<S, 32, 0, stream>>>(2, nblk, pts, gpart, dpart, st, nullptr);
-      for (int it = 0; it < MES_NEWTON; ++it) {
-        mes_eval_kernel<<<gq, 256, 0, stream>>>(A.mu, A.sd, m, pts, 3, 1, gpart, dpart);
-        mes_control_kernel<<<S, 32, 0, stream>>>(3, nblk, pts, gpart, dpart, st, nullptr);
-      }
-      mes_control_kernel<<<S, 32, 0, stream>>>(4, nblk, pts, gpart, dpart, st, A.mes_fit);
       dim3 gm((m + 127) / 128, S);
-      mes_epilogue_kernel<<<gm, 128, A.K * sizeof(double), stream>>>(A.mu, A.sd, m, A.u32, A.K, st, A.per_theta);
+      mes_epilogue_kernel<<<gm, 128, A.K * sizeof(double), stream>>>(A.mu, A.sd, m, A.u32, A.K,
+                                                                     A.mes_fit ? A.mes_fit : w.fit, A.per_theta);
     } break;
     default: return cudaErrorInvalidValue;
   }
-  finite_rows_kernel<<<S, 1024, 0, stream>>>(A.per_theta, m, stats, A.skipped);
-  combine_kernel<<<(m + 255) / 256, 256, 0, stream>>>(A.per_theta, S, m, A.skipped, A.out);
+  finite_rows_kernel<<<S, 1024, 0, stream>>>(A.per_theta, m, w.stats, A.skipped);
   return cudaGetLastError();
+}
+
+cudaError_t launch_acq_combine(const double* per_theta, int S, int m, const int32_t* skipped, double* out,
+                               cudaStream_t stream) {
+  combine_kernel<<<(m + 255) / 256, 256, 0, stream>>>(per_theta, S, m, skipped, out);
+  return cudaGetLastError();
+}
+
+// single-GPU composition: stats -> (fit | EI argmax) -> per-theta values -> finite-guarded mean
+cudaError_t launch_acq(const AcqArgs& A, cudaStream_t stream) {
+  if (A.S <= 0) return cudaSuccess;
+  cudaError_t e = launch_acq_stats(A.mu, A.sd, A.S, A.m, nullptr, A.scratch, stream);
+  if (e != cudaSuccess) return e;
+  AcqArgs B = A;
+  if (A.kind == BGP_ACQ_MES && !A.mes_fit_given) {
+    e = launch_mes_fit(A.mu, A.sd, A.S, A.m, A.mes_fit, A.scratch, stream);
+    if (e != cudaSuccess) return e;
+  }
+  if (A.kind == BGP_ACQ_TTEI && !A.ref) {
+    e = launch_ei_best(A.mu, A.sd, A.S, A.m, A.p0, A.yopt, 0, nullptr, A.scratch, stream);
+    if (e != cudaSuccess) return e;
+  }
+  e = launch_acq_per_theta(B, stream);
+  if (e != cudaSuccess) return e;
+  return launch_acq_combine(A.per_theta, A.S, A.m, A.skipped, A.out, stream);
 }
 
 __global__ void argmax_final_kernel(const double* __restrict__ v, int m, long long* __restrict__ idx) {

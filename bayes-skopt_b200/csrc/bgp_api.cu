@@ -327,13 +327,74 @@ int bgp_acq_sweep(bgp_handle_t h, int kind, const double* mu_dev, const double* 
                   const float* g32_dev, int K, double* per_theta_dev, double* out_dev, int32_t* skipped_dev,
                   double* mes_fit_dev, void* stream) {
   CHECK_H(h);
-  if (!mu_dev || !sd_dev || S <= 0 || m <= 0 || !per_theta_dev || !out_dev || !skipped_dev)
+  if (!mu_dev || !sd_dev || S <= 0 || S > 1024 || m <= 0 || !per_theta_dev || !out_dev || !skipped_dev)
     return fail("bad acquisition arguments");
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(h->acq_scratch.ensure(sizeof(double) * bgp::acq_scratch_doubles(S, m)));
   bgp::AcqArgs A{kind, mu_dev, sd_dev, S, m, p0, g32_dev, K, per_theta_dev, out_dev, skipped_dev, mes_fit_dev,
-                 h->acq_scratch.as<double>()};
+                 h->acq_scratch.as<double>(), nullptr, nullptr, 0};
   CUDA_TRY(bgp::launch_acq(A, (cudaStream_t)stream));
+  return 0;
+}
+
+int bgp_acq_stats(bgp_handle_t h, const double* mu_dev, const double* sd_dev, int S, int m, double* stats_dev,
+                  void* stream) {
+  CHECK_H(h);
+  if (!mu_dev || !sd_dev || S <= 0 || S > 1024 || m <= 0 || !stats_dev) return fail("bad stats arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(h->acq_scratch.ensure(sizeof(double) * bgp::acq_scratch_doubles(S, m)));
+  CUDA_TRY(bgp::launch_acq_stats(mu_dev, sd_dev, S, m, stats_dev, h->acq_scratch.as<double>(), (cudaStream_t)stream));
+  return 0;
+}
+
+int bgp_mes_fit(bgp_handle_t h, const double* mu_dev, const double* sd_dev, int S, int m, double* fit_dev,
+                void* stream) {
+  CHECK_H(h);
+  if (!mu_dev || !sd_dev || S <= 0 || S > 1024 || m <= 0 || !fit_dev) return fail("bad mes-fit arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(h->acq_scratch.ensure(sizeof(double) * bgp::acq_scratch_doubles(S, m)));
+  CUDA_TRY(bgp::launch_acq_stats(mu_dev, sd_dev, S, m, nullptr, h->acq_scratch.as<double>(), (cudaStream_t)stream));
+  CUDA_TRY(bgp::launch_mes_fit(mu_dev, sd_dev, S, m, fit_dev, h->acq_scratch.as<double>(), (cudaStream_t)stream));
+  return 0;
+}
+
+int bgp_ei_best(bgp_handle_t h, const double* mu_dev, const double* sd_dev, int S, int m, double p0,
+                const double* yopt_dev, int64_t index_offset, double* ref_dev, void* stream) {
+  CHECK_H(h);
+  if (!mu_dev || !sd_dev || S <= 0 || S > 1024 || m <= 0 || !ref_dev) return fail("bad ei-best arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(h->acq_scratch.ensure(sizeof(double) * bgp::acq_scratch_doubles(S, m)));
+  if (!yopt_dev)
+    CUDA_TRY(bgp::launch_acq_stats(mu_dev, sd_dev, S, m, nullptr, h->acq_scratch.as<double>(), (cudaStream_t)stream));
+  CUDA_TRY(bgp::launch_ei_best(mu_dev, sd_dev, S, m, p0, yopt_dev, index_offset, ref_dev,
+                               h->acq_scratch.as<double>(), (cudaStream_t)stream));
+  return 0;
+}
+
+int bgp_acq_per_theta(bgp_handle_t h, int kind, const double* mu_dev, const double* sd_dev, int S, int m,
+                      double p0, const double* yopt_dev, const double* ref_dev, const float* g32_dev, int K,
+                      const double* fit_dev, double* per_theta_dev, int32_t* skipped_dev, void* stream) {
+  CHECK_H(h);
+  if (!mu_dev || !sd_dev || S <= 0 || S > 1024 || m <= 0 || !per_theta_dev || !skipped_dev)
+    return fail("bad per-theta acquisition arguments");
+  if (kind == BGP_ACQ_MES && !fit_dev) return fail("MES needs the Gumbel fit (bgp_mes_fit)");
+  if (kind == BGP_ACQ_TTEI && !ref_dev) return fail("TTEI needs the EI maximiser (bgp_ei_best)");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(h->acq_scratch.ensure(sizeof(double) * bgp::acq_scratch_doubles(S, m)));
+  if (kind == BGP_ACQ_EI && !yopt_dev && isnan(p0))
+    CUDA_TRY(bgp::launch_acq_stats(mu_dev, sd_dev, S, m, nullptr, h->acq_scratch.as<double>(), (cudaStream_t)stream));
+  bgp::AcqArgs A{kind, mu_dev, sd_dev, S, m, p0, g32_dev, K, per_theta_dev, nullptr, skipped_dev,
+                 const_cast<double*>(fit_dev), h->acq_scratch.as<double>(), yopt_dev, ref_dev, 1};
+  CUDA_TRY(bgp::launch_acq_per_theta(A, (cudaStream_t)stream));
+  return 0;
+}
+
+int bgp_acq_combine(bgp_handle_t h, const double* per_theta_dev, int S, int m, const int32_t* skipped_dev,
+                    double* out_dev, void* stream) {
+  CHECK_H(h);
+  if (!per_theta_dev || S <= 0 || m <= 0 || !skipped_dev || !out_dev) return fail("bad combine arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(bgp::launch_acq_combine(per_theta_dev, S, m, skipped_dev, out_dev, (cudaStream_t)stream));
   return 0;
 }
 

@@ -81,16 +81,28 @@ struct AcqArgs {
   const double* sd;
   int S, m;
   double p0;
-  const float* u32;
+  const float* u32;    // float32 standard Gumbel variates, S x K (MES)
   int K;
-  double* per_theta;   // S x m scratch / output
+  double* per_theta;   // S x m output
   double* out;         // m
   int32_t* skipped;    // S
-  double* mes_fit;     // S x 5 or null
+  double* mes_fit;     // S x 5 (a, b, q1, med, q2): output of the search, or input when mes_fit_given
   double* scratch;     // workspace (see acq_scratch_doubles)
+  const double* yopt;  // optional per-theta y_opt (S) overriding the local min mu (EI / TTEI)
+  const double* ref;   // optional per-theta {ei, index, mu, sd} of the global EI maximiser (TTEI)
+  int mes_fit_given;
 };
 size_t acq_scratch_doubles(int S, int m);
 cudaError_t launch_acq(const AcqArgs& A, cudaStream_t stream);
+cudaError_t launch_acq_stats(const double* mu, const double* sd, int S, int m, double* stats_out, double* scratch,
+                             cudaStream_t stream);
+cudaError_t launch_mes_fit(const double* mu, const double* sd, int S, int m, double* fit_out, double* scratch,
+                           cudaStream_t stream);
+cudaError_t launch_ei_best(const double* mu, const double* sd, int S, int m, double p0, const double* yopt,
+                           long long index_offset, double* ref_out, double* scratch, cudaStream_t stream);
+cudaError_t launch_acq_per_theta(const AcqArgs& A, cudaStream_t stream);
+cudaError_t launch_acq_combine(const double* per_theta, int S, int m, const int32_t* skipped, double* out,
+                               cudaStream_t stream);
 struct PostCovArgs {
   const double* X;       // unused (kept for symmetry)
   const double* theta;   // 1 x p

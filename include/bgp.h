@@ -172,6 +172,29 @@ enum bgp_acq_kind { BGP_ACQ_EI = 1, BGP_ACQ_TTEI = 2, BGP_ACQ_MEAN = 3, BGP_ACQ_
 int bgp_acq_sweep(bgp_handle_t h, int kind, const double* mu_dev, const double* sd_dev, int S,
                   int m, double p0, const float* g32_dev, int K, double* per_theta_dev,
                   double* out_dev, int32_t* skipped_dev, double* mes_fit_dev, void* stream);
+/* The same epilogues in stages, for hosts that shard the candidates over several GPUs and
+ * exchange the per-theta scalars in between (small all-reduces / all-gathers):
+ *   bgp_acq_stats     stats[s] = {min mu, min(-mu-3sd), max(-mu+5sd), all-finite}        (S x 4)
+ *   bgp_mes_fit       Gumbel fit {a, b, q1, med, q2} of the max-value distribution from the
+ *                     moments of ALL candidates (bask/acquisition.py:235-252)              (S x 5)
+ *   bgp_ei_best       ref[s] = {max EI, global index, mu, sd} of this shard's EI maximiser  (S x 4)
+ *   bgp_acq_per_theta per-theta values of this shard given the global y_opt (yopt_dev, S), the
+ *                     global EI maximiser (ref_dev, TTEI) or the global Gumbel fit (fit_dev, MES);
+ *                     skipped[s] = 1 when a value of theta s is non-finite on this shard
+ *   bgp_acq_combine   out[i] = (1/S) sum_{s not skipped} per_theta[s, i]                          */
+int bgp_acq_stats(bgp_handle_t h, const double* mu_dev, const double* sd_dev, int S, int m,
+                  double* stats_dev, void* stream);
+int bgp_mes_fit(bgp_handle_t h, const double* mu_dev, const double* sd_dev, int S, int m,
+                double* fit_dev, void* stream);
+int bgp_ei_best(bgp_handle_t h, const double* mu_dev, const double* sd_dev, int S, int m, double p0,
+                const double* yopt_dev, int64_t index_offset, double* ref_dev, void* stream);
+int bgp_acq_per_theta(bgp_handle_t h, int kind, const double* mu_dev, const double* sd_dev, int S,
+                      int m, double p0, const double* yopt_dev, const double* ref_dev,
+                      const float* g32_dev, int K, const double* fit_dev, double* per_theta_dev,
+                      int32_t* skipped_dev, void* stream);
+int bgp_acq_combine(bgp_handle_t h, const double* per_theta_dev, int S, int m,
+                    const int32_t* skipped_dev, double* out_dev, void* stream);
+
 /* argmax with numpy tie-breaking (first maximum), bask/optimizer.py:374-376 */
 int bgp_argmax(bgp_handle_t h, const double* v_dev, int m, int64_t* idx_dev, void* stream);
 
