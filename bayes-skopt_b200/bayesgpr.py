@@ -245,7 +245,7 @@ class BayesGPR:
     # ------------------------------------------------------------------ MCMC
     def sample(self, X=None, y=None, noise_vector=None, n_threads=1, n_desired_samples=100, n_burnin=0,
                n_thin=1, n_walkers_per_thread=100, progress=False, priors=None, warp_priors=None,
-               position=None, add=False, n_walkers=None, **kwargs):
+               position=None, add=False, n_walkers=None, process_group=None, **kwargs):
         """Ensemble MCMC over the hyper-posterior, entirely on device (bask/bayesgpr.py:381-548).
         ``**kwargs`` are the emcee.EnsembleSampler keywords of the reference; ``a`` (stretch
         scale) is honoured, ``vectorize``/``threads`` are meaningless here and ignored."""
@@ -310,7 +310,14 @@ class BayesGPR:
         e = self._eng()
         table, host_fn = as_device_priors(priors, n_dim)
         e.set_priors(table)
-        if host_fn is None:
+        if host_fn is None and process_group is not None and \
+                __import__("torch").distributed.get_world_size(process_group) > 1:
+            # walkers sharded over the ranks of the group (one all-gather of W/2 log-probs per half
+            # step); every rank ends up with the identical chain
+            from .distributed import sharded_mcmc
+            chain_steps, pos_out, accepted = sharded_mcmc(e, pos, n_samples, seed, a, process_group)
+            self._acceptance = accepted / max(n_samples, 1)
+        elif host_fn is None:
             buf = e.mcmc(pos, n_samples, seed, a=a, buffers=self._mc_buffers)
             self._mc_buffers = buf
             e.sync()
@@ -372,7 +379,7 @@ class BayesGPR:
     # ------------------------------------------------------------------ fit
     def fit(self, X, y, noise_vector=None, n_threads=1, n_desired_samples=100, n_burnin=10,
             n_walkers_per_thread=100, progress=True, priors=None, warp_priors=None, position=None,
-            **kwargs):
+            process_group=None, **kwargs):
         """MAP start (L-BFGS-B over device LML evaluations) followed by ``sample``
         (bask/bayesgpr.py:550-620 -> skopt/sklearn fit, sklearn:_gpr.py:233-368)."""
         self.kernel = self._kernel
@@ -383,7 +390,8 @@ class BayesGPR:
         self._fit_map(X, y)
         self.sample(n_threads=n_threads, n_desired_samples=n_desired_samples, n_burnin=n_burnin,
                     n_walkers_per_thread=n_walkers_per_thread, progress=progress, priors=priors,
-                    warp_priors=warp_priors, position=position, add=False, **kwargs)
+                    warp_priors=warp_priors, position=position, add=False, process_group=process_group,
+                    **kwargs)
         return self
 
     def _fit_map(self, X, y):

@@ -26,7 +26,7 @@ import torch.distributed as dist
 
 from . import _lib
 
-__all__ = ["shard_bounds", "ShardedSweep", "DeviceBackend"]
+__all__ = ["shard_bounds", "ShardedSweep", "DeviceBackend", "sharded_mcmc"]
 
 
 def shard_bounds(m, world, rank):
@@ -52,13 +52,14 @@ class DeviceBackend:
 
     def moments(self, thetas, X_block):
         e = self.e
-        th = e.to_dev(thetas)
+        th = thetas if torch.is_tensor(thetas) else e.to_dev(thetas)
         f = e.factorize(th)
         if np.any(e.to_host(f.info) != 0):
             raise np.linalg.LinAlgError("The kernel is not returning a positive definite matrix.")
         y_mean = float(np.atleast_1d(self.gpr.y_train_mean_)[0])
         y_std = float(np.atleast_1d(self.gpr.y_train_std_)[0])
-        mu, sd, _, _ = e.predict(f, e.to_dev(X_block), noise_off=True, y_mean=y_mean, y_std=y_std)
+        Xd = X_block.contiguous() if torch.is_tensor(X_block) else e.to_dev(X_block)
+        mu, sd, _, _ = e.predict(f, Xd, noise_off=True, y_mean=y_mean, y_std=y_std)
         e.sync()
         return mu, sd
 
@@ -88,7 +89,7 @@ class DeviceBackend:
         S, m = mu.shape
         vals = self.e.empty(S, m)
         skipped = self.e.empty(S, dtype=torch.int32)
-        g = None if gumbel is None else self.e.to_dev(gumbel, dtype=torch.float32)
+        g = None if gumbel is None else (gumbel if torch.is_tensor(gumbel) else self.e.to_dev(gumbel, dtype=torch.float32))
         self._run(self.e.lib.bgp_acq_per_theta, kind, mu.data_ptr(), sd.data_ptr(), S, m, float(p0),
                   None if yopt is None else yopt.data_ptr(), None if ref is None else ref.data_ptr(),
                   None if g is None else g.data_ptr(), 0 if g is None else g.shape[1],
@@ -108,8 +109,8 @@ class ShardedSweep:
     """evaluate the built-in (mu, std) acquisitions over candidates sharded across the ranks of
     `group`.  Every rank passes the same arguments and gets the same (n_acq, m) result."""
 
-    def __init__(self, backend, group=None):
-        self.b, self.group = backend, group
+    def __init__(self, backend, group=None, keep_on_device=False):
+        self.b, self.group, self.keep_on_device = backend, group, keep_on_device
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
 
@@ -139,6 +140,7 @@ class ShardedSweep:
         mu, sd = self.b.moments(thetas, X[lo:hi])
         S = mu.shape[0]
         out = np.zeros((len(acquisitions), m))
+        out_dev = []
         yopt = None
         fit = None
         for j, (kind, p0) in enumerate(acquisitions):
@@ -174,5 +176,61 @@ class ShardedSweep:
                 dist.all_reduce(skipped, op=dist.ReduceOp.MAX, group=self.group)
             local = self.b.combine(vals, skipped)
             full = self._allgather_cols(local[None, :], sizes)[0]
-            out[j] = full.cpu().numpy()
-        return out
+            if self.keep_on_device:
+                out_dev.append(full)
+            else:
+                out[j] = full.cpu().numpy()
+        return out_dev if self.keep_on_device else out
+
+
+def sharded_mcmc(engine, pos, n_steps, seed, a, group, lp_extra_fn=None):
+    """Walker-sharded stretch move: every rank regenerates the identical red/blue split,
+    proposals and accept draws from the shared Philox stream (no broadcast), evaluates the
+    log-posterior of ITS slice of the W/2 proposals of each half step, and one all-gather of
+    W/2 doubles per half step makes the accept test identical everywhere.  Returns host
+    (chain_steps (T, W, p), final pos (W, p), acceptance counts (W,))."""
+    import ctypes as C
+    e = engine
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    W, p = pos.shape
+    lib, h, st = e.lib, e.h, e._st
+    P = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    sd = C.c_uint64(int(seed) & (2 ** 64 - 1))
+    with torch.cuda.stream(e.stream):
+        d_pos = e.to_dev(pos)
+        lo, hi = shard_bounds(W, world, rank)
+        sizes = [shard_bounds(W, world, r)[1] - shard_bounds(W, world, r)[0] for r in range(world)]
+        lp_loc, _, _ = e.logprob_dev(d_pos[lo:hi].contiguous())
+        d_lp = _allgather_1d(lp_loc, sizes, group)
+        colour = e.empty(W, dtype=torch.int32)
+        movers = e.empty(W, dtype=torch.int32)
+        q, fac = e.empty(W, p), e.empty(W)
+        acc = torch.zeros(W, dtype=torch.int32, device=e.device)
+        chain = e.empty(n_steps, W, p)
+        lpc = e.empty(n_steps, W)
+        for t in range(n_steps):
+            _lib.check(lib.bgp_mcmc_split(h, W, sd, t, P(colour), st), "bgp_mcmc_split")
+            for half in (0, 1):
+                ns = (W + 1) // 2 if half == 0 else W // 2
+                _lib.check(lib.bgp_mcmc_propose(h, P(d_pos), P(colour), W, half, float(a), sd, t, P(q), P(fac),
+                                                P(movers), st), "bgp_mcmc_propose")
+                lo, hi = shard_bounds(ns, world, rank)
+                sizes = [shard_bounds(ns, world, r)[1] - shard_bounds(ns, world, r)[0] for r in range(world)]
+                nlp_loc, _, _ = e.logprob_dev(q[lo:hi])
+                nlp = _allgather_1d(nlp_loc, sizes, group)
+                _lib.check(lib.bgp_mcmc_accept(h, P(d_pos), P(d_lp), P(q), P(fac), P(nlp), P(movers), W, half, sd,
+                                               t, P(acc), P(chain[t]) if half == 1 else None,
+                                               P(lpc[t]) if half == 1 else None, st), "bgp_mcmc_accept")
+                e.launches += 5
+        e.sync()
+        return chain.cpu().numpy(), d_pos.cpu().numpy(), acc.cpu().numpy()
+
+
+def _allgather_1d(t, sizes, group):
+    """ragged all-gather of 1-D tensors (sizes[r] elements from rank r) -> concatenation"""
+    mmax = max(sizes)
+    pad = torch.zeros(mmax, dtype=t.dtype, device=t.device)
+    pad[: t.shape[0]] = t
+    parts = [torch.empty_like(pad) for _ in sizes]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([p_[:sz] for p_, sz in zip(parts, sizes)]).contiguous()

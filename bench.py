@@ -178,17 +178,20 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     w = W.config3()
     m_local = len(w.candidates)
-    # weak scaling: every rank sweeps its own block of 10k candidates; the (tiny) MCMC is replicated
-    # with identical Philox streams, so no data-path collective is needed for it
-    cands = np.random.RandomState(21 + rank).uniform(size=(m_local, w.d)) if world > 1 else w.candidates
+    # weak scaling: the candidate set grows with the number of GPUs (10k per rank) and is sharded by
+    # bask_b200.distributed; the (tiny) MCMC is replicated with identical Philox streams, so the only
+    # collectives are the sweep's per-theta scalars and the final all-gather of acquisition values
+    cands = np.random.RandomState(21).uniform(size=(m_local * world, w.d)) if world > 1 else w.candidates
     gp = bask_b200.BayesGPR(kernel=construct_default_kernel(list(range(w.d))), normalize_y=True,
                             random_state=0, device=local)
-    gp.fit(w.X, w.y, noise_vector=w.noise_vector, n_desired_samples=w.n_desired_samples, n_burnin=w.n_burnin,
-           n_walkers_per_thread=w.n_walkers, progress=False)
+    pg = dist.group.WORLD if world > 1 else None
+    Wk = w.n_walkers * world       # weak scaling: 128 walkers per GPU, sharded by bask_b200.distributed
+    gp.fit(w.X, w.y, noise_vector=w.noise_vector, n_desired_samples=Wk, n_burnin=w.n_burnin,
+           n_walkers_per_thread=Wk, progress=False, process_group=pg)
     e = gp._eng()
     mes = bask_b200.MaxValueSearch()
     K = w.acq_kwargs["n_min_samples"]
-    S, T, Wk = w.n_theta_samples, w.n_steps, w.n_walkers
+    S, T = w.n_theta_samples, w.n_steps
 
     def barrier():
         torch.cuda.synchronize()
@@ -201,6 +204,10 @@ def run_b200(args):
     # ---------------- device-resident cycle (inputs already in HBM)
     pos_dev = e.to_dev(gp.pos_)
     Xc_dev = e.to_dev(cands)
+    sweep = None
+    if world > 1:
+        from bask_b200.distributed import DeviceBackend, ShardedSweep
+        sweep = ShardedSweep(DeviceBackend(gp), dist.group.WORLD, keep_on_device=True)
     picks = np.random.RandomState(1).choice(len(gp.chain_), replace=False, size=S)
     g32 = np.stack([bask_b200.acquisition.gumbel32_like_reference(K) for _ in range(S)])
     g32_dev = e.to_dev(g32, dtype=torch.float32)
@@ -210,10 +217,18 @@ def run_b200(args):
     def device_cycle(seed):
         with torch.cuda.stream(e.stream):
             flush.zero_()
-        b = e.mcmc(pos_dev, T, seed, buffers=bufs["mc"])
-        bufs["mc"] = b
-        with torch.cuda.stream(e.stream):
-            th = b["chain"][-1][torch.as_tensor(picks % Wk, device=e.device)].contiguous()
+        if world > 1:
+            from bask_b200.distributed import sharded_mcmc
+            chain_h, _pos_h, _acc = sharded_mcmc(e, gp.pos_, T, seed, 2.0, pg)
+            th = e.to_dev(chain_h[-1][picks % Wk])
+        else:
+            b = e.mcmc(pos_dev, T, seed, buffers=bufs["mc"])
+            bufs["mc"] = b
+            with torch.cuda.stream(e.stream):
+                th = b["chain"][-1][torch.as_tensor(picks % Wk, device=e.device)].contiguous()
+        if sweep is not None:
+            out = sweep.evaluate(Xc_dev, th, [(_lib.ACQ_MES, float("nan"))], {0: g32_dev})[0]
+            return e.argmax(out.contiguous())
         f = e.factorize(th)
         mu, sd, _, _ = e.predict(f, Xc_dev, noise_off=True, y_mean=y_mean, y_std=y_std)
         out, _, _, _ = e.acq(_lib.ACQ_MES, mu, sd, gumbel32=g32_dev)
@@ -238,9 +253,10 @@ def run_b200(args):
     def e2e_cycle(seed):
         with torch.cuda.stream(e.stream):
             flush.zero_()
-        gp.sample(w.X, w.y, noise_vector=w.noise_vector, n_desired_samples=w.n_desired_samples,
-                  n_burnin=w.n_burnin, n_walkers_per_thread=w.n_walkers)
+        gp.sample(w.X, w.y, noise_vector=w.noise_vector, n_desired_samples=Wk, n_burnin=w.n_burnin,
+                  n_walkers_per_thread=Wk, process_group=pg)
         vals = bask_b200.evaluate_acquisitions(cands, gp, (mes,), n_samples=S, random_state=seed,
+                                               process_group=dist.group.WORLD if world > 1 else None,
                                                **w.acq_kwargs)[0]
         return int(np.argmax(vals))
 
@@ -252,11 +268,11 @@ def run_b200(args):
         e2e_cycle(10 + i)
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
-    h2d = 8 * (w.X.size + 2 * w.n + Wk * (w.d + 2) + cands.size + S * (w.d + 2)) + 4 * S * K
-    d2h = 8 * (T * Wk * (w.d + 2) + Wk * (w.d + 2) + m_local + 1 + S)
+    h2d = 8 * (w.X.size + 2 * w.n + Wk * (w.d + 2) + cands.size // world + S * (w.d + 2)) + 4 * S * K
+    d2h = 8 * (T * Wk * (w.d + 2) + Wk * (w.d + 2) + m_local * world + 1 + S)
 
     # ---------------- roofline of the dominant kernel, timed alone on its launch stream
-    nb = (Wk + 1) // 2
+    nb = (w.n_walkers + 1) // 2
     th64 = e.to_dev(gp.chain_[:nb])
     for _ in range(3):
         e.logprob_dev(th64)
@@ -275,6 +291,7 @@ def run_b200(args):
     # sweep kernel
     th = e.to_dev(gp.chain_[picks])
     f = e.factorize(th)
+    Xc_dev = Xc_dev[:m_local].contiguous()
     for _ in range(2):
         e.predict(f, Xc_dev, noise_off=True, y_mean=y_mean, y_std=y_std)
     e.sync()
@@ -292,14 +309,14 @@ def run_b200(args):
     dev_ms, e2e_ms = [float(v) for v in times.cpu()]
 
     if rank == 0:
-        evals = w.n_logprob_evals * world
+        evals = Wk * (1 + T)          # distinct log-posterior evaluations per cycle, all ranks together
         line = {"metric": METRIC, "value": evals / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": w.name, "n_obs": w.n, "dims": w.d, "walkers": Wk, "mcmc_steps": T,
+                "config": {"workload": w.name, "n_obs": w.n, "dims": w.d, "walkers": Wk, "walkers_per_gpu": w.n_walkers, "mcmc_steps": T,
                            "theta_samples": S, "candidates_per_gpu": m_local, "acquisition": w.acquisition,
                            "l2": "256 MiB memset between steps (inside the timed region)",
-                           "multi_gpu": "candidates sharded per rank, MCMC replicated (identical Philox streams)"},
+                           "multi_gpu": "weak scaling: 128 walkers and 10k candidates per GPU; walkers sharded with one all-gather of W/2 log-probs per half step, candidates sharded with per-theta scalar exchanges"},
                 "clocks": clocks,
                 "e2e": {"value": evals / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
