@@ -192,7 +192,7 @@ class Engine:
         info = self.empty(B, dtype=torch.int32)
         check(self.lib.bgp_logprob_batched(self.h, _ptr(thetas_dev), B, _ptr(lp_extra_dev), _ptr(lp),
                                            _ptr(lml), _ptr(info), self._st), "bgp_logprob_batched")
-        self.launches += 1
+        self.launches += 3      # scale_x + gram + chol per wave of <= 148 thetas
         return lp, lml, info
 
     def logprob(self, thetas, lp_extra=None):
@@ -212,7 +212,7 @@ class Engine:
         info = self.empty(S, dtype=torch.int32)
         check(self.lib.bgp_factorize_batched(self.h, _ptr(th), S, _ptr(slabs), _ptr(z), _ptr(lml),
                                              _ptr(info), self._st), "bgp_factorize_batched")
-        self.launches += 1
+        self.launches += 3
         return Factor(th, slabs, z, lml, info)
 
     def extract(self, factor, index, what):
@@ -250,7 +250,7 @@ class Engine:
         check(self.lib.bgp_acq_sweep(self.h, kind, _ptr(mu), _ptr(sd), S, m, float(p0), _ptr(gumbel32), K,
                                      _ptr(per_theta), _ptr(out), _ptr(skipped), _ptr(fit), self._st),
               "bgp_acq_sweep")
-        self.launches += {_lib.ACQ_EI: 4, _lib.ACQ_TTEI: 6, _lib.ACQ_MEAN: 4, _lib.ACQ_LCB: 4,
+        self.launches += {_lib.ACQ_EI: 4, _lib.ACQ_TTEI: 7, _lib.ACQ_MEAN: 4, _lib.ACQ_LCB: 4,
                           _lib.ACQ_MES: 29}[kind]
         return out, per_theta, skipped, fit
 
@@ -274,5 +274,5 @@ class Engine:
         check(self.lib.bgp_mcmc_run(self.h, _ptr(buffers["pos"]), _ptr(buffers["lp"]), W, n_steps, float(a),
                                     C.c_uint64(int(seed) & (2 ** 64 - 1)), _ptr(buffers["chain"]),
                                     _ptr(buffers["lpc"]), _ptr(buffers["acc"]), self._st), "bgp_mcmc_run")
-        self.launches += 2 + 7 * n_steps
+        self.launches += 3 + 11 * n_steps   # initial log-posterior + per step: split, 2 x (propose, 3, accept)
         return buffers

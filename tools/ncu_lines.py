@@ -8,7 +8,17 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 rows = list(csv.reader(io.StringIO(out)))
 hdr = next(r for r in rows if "# Samples" in r)
 isamp, isrc = hdr.index("# Samples"), hdr.index("Source")
-inst = [(r[isrc].strip(), int(r[isamp])) for r in rows if len(r) > isamp and r[isamp].isdigit()]
+# the CSV holds one section per captured launch ("Kernel Name", name): take the first match
+want = kname.replace("ILi", "<").split("<")[0].split("_ZN3bgp")[-1].lstrip("0123456789")
+inst, take = [], False
+for r in rows:
+    if r and r[0] == "Kernel Name":
+        if take and inst:
+            break
+        take = want in r[1]
+        continue
+    if take and len(r) > isamp and r[isamp].isdigit():
+        inst.append((r[isrc].strip(), int(r[isamp])))
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, capture_output=True)
 lines = None
