@@ -127,30 +127,18 @@ __device__ __noinline__ int warp_potrf32(double* __restrict__ D, double* __restr
   return fail;
 }
 
-// stage rows [c0, c0+32) x the columns of panels [j0, j0+kc) of L into shared memory
+// stage rows [c0, c0+32) x the columns of panels [j0, j0+kc) of L into shared memory with
+// cp.async (16-byte LDGSTS, L2 only): every copy of a thread is in flight before the first wait,
+// so the stage costs about one L2 round trip instead of one per loop iteration
 __device__ __forceinline__ void stage_block_row(const double* slab, const SlabGeom& G, double* Bs, int bstride,
                                                 int c0, int j0, int kc, int tid, int nthreads) {
-  // four independent 16-byte loads in flight per thread before the first store
-  for (int idx0 = tid; idx0 < 512 * kc; idx0 += 4 * nthreads) {
-    double2 v[4];
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      const int idx = idx0 + s * nthreads;
-      if (idx < 512 * kc) {
-        const int c2 = idx & 15, row = (idx >> 4) & 31, jj = idx >> 9;
-        v[s] = *reinterpret_cast<const double2*>(
-            slab + G.off(j0 + jj) + (size_t)(c0 + row - 32 * (j0 + jj)) * 32 + 2 * c2);
-      }
-    }
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      const int idx = idx0 + s * nthreads;
-      if (idx < 512 * kc) {
-        const int c2 = idx & 15, row = (idx >> 4) & 31, jj = idx >> 9;
-        *reinterpret_cast<double2*>(Bs + (size_t)row * bstride + 32 * jj + 2 * c2) = v[s];
-      }
-    }
+  for (int idx = tid; idx < 512 * kc; idx += nthreads) {
+    const int c2 = idx & 15, row = (idx >> 4) & 31, jj = idx >> 9;
+    const double* src = slab + G.off(j0 + jj) + (size_t)(c0 + row - 32 * (j0 + jj)) * 32 + 2 * c2;
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(Bs + (size_t)row * bstride + 32 * jj + 2 * c2);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
   }
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
 struct TileSet {
@@ -166,48 +154,58 @@ template <int NTL>
 __device__ __forceinline__ void k_chunk(double (&acc)[4][4][2], const TileSet& TS, const double* slab,
                                         const SlabGeom& G, const double* Bs, int bstride, int j0, int kc,
                                         int r, int q) {
+  // L2 round trips cost ~1000 cycles here while one 8-column step is only NTL x 128 cycles of DMMA
+  // issue, so the A operand runs PF steps ahead in a register ring (statically indexed)
+  constexpr int PF = NTL == 1 ? 8 : (NTL == 2 ? 4 : 3);
   int jmin = j0 + kc;
 #pragma unroll
   for (int t = 0; t < NTL; ++t) jmin = min(jmin, TS.js[t]);
   const int jbeg = max(j0, jmin), jend = j0 + kc;
   if (jbeg >= jend) return;
   const int steps = 4 * (jend - jbeg);
-  const double* ap[NTL];
-  double2 nxt[NTL];
-  int j = jbeg, c8p = 0;
+  double2 ring[PF][NTL];
 #pragma unroll
-  for (int t = 0; t < NTL; ++t) {
-    ap[t] = slab + G.off(j) + (size_t)(TS.rb[t] + r - 32 * j) * 32 + 2 * q;
-    nxt[t] = (j >= TS.js[t]) ? *reinterpret_cast<const double2*>(ap[t]) : make_double2(0.0, 0.0);
-  }
-  for (int st = 0; st < steps; ++st) {
-    double2 av[NTL];
-#pragma unroll
-    for (int t = 0; t < NTL; ++t) av[t] = nxt[t];
-    const int bcol = 32 * (j - j0) + 8 * c8p + 2 * q;
-    if (++c8p == 4) {
-      c8p = 0; ++j;
-#pragma unroll
-      for (int t = 0; t < NTL; ++t) ap[t] = slab + G.off(j) + (size_t)(TS.rb[t] + r - 32 * j) * 32 + 2 * q;
-    } else {
-#pragma unroll
-      for (int t = 0; t < NTL; ++t) ap[t] += 8;
-    }
-    if (st + 1 < steps) {
-#pragma unroll
-      for (int t = 0; t < NTL; ++t)
-        nxt[t] = (j >= TS.js[t]) ? *reinterpret_cast<const double2*>(ap[t]) : make_double2(0.0, 0.0);
-    }
-    double2 bv[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      bv[u] = *reinterpret_cast<const double2*>(Bs + (size_t)(8 * u + r) * bstride + bcol);
+  for (int s = 0; s < PF; ++s) {
+    const int jj = jbeg + (s >> 2);
 #pragma unroll
     for (int t = 0; t < NTL; ++t) {
+      ring[s][t] = make_double2(0.0, 0.0);
+      if (s < steps && jj >= TS.js[t])
+        ring[s][t] = *reinterpret_cast<const double2*>(
+            slab + G.off(jj) + (size_t)(TS.rb[t] + r - 32 * jj) * 32 + 8 * (s & 3) + 2 * q);
+    }
+  }
+  for (int st0 = 0; st0 < steps; st0 += PF) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) dmma(acc[t][u], av[t].x, bv[u].x);
+    for (int s = 0; s < PF; ++s) {
+      const int st = st0 + s;
+      if (st < steps) {
+        const int jcur = jbeg + (st >> 2);
+        double2 av[NTL];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) dmma(acc[t][u], av[t].y, bv[u].y);
+        for (int t = 0; t < NTL; ++t) av[t] = ring[s][t];
+        const int sn = st + PF, jn = jbeg + (sn >> 2);
+        if (sn < steps) {
+#pragma unroll
+          for (int t = 0; t < NTL; ++t)
+            ring[s][t] = (jn >= TS.js[t]) ? *reinterpret_cast<const double2*>(
+                                                slab + G.off(jn) + (size_t)(TS.rb[t] + r - 32 * jn) * 32 +
+                                                8 * (sn & 3) + 2 * q)
+                                          : make_double2(0.0, 0.0);
+        }
+        const int bcol = 32 * (jcur - j0) + 8 * (st & 3) + 2 * q;
+        double2 bv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          bv[u] = *reinterpret_cast<const double2*>(Bs + (size_t)(8 * u + r) * bstride + bcol);
+#pragma unroll
+        for (int t = 0; t < NTL; ++t) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) dmma(acc[t][u], av[t].x, bv[u].x);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) dmma(acc[t][u], av[t].y, bv[u].y);
+        }
+      }
     }
   }
 }
@@ -302,6 +300,44 @@ __device__ __forceinline__ void finish_tiles(double (&acc)[4][4][2], const TileS
   }
 }
 
+// Dblk = init(diagonal block kk) - sum of the four partial products (when kk > 0)
+__device__ __forceinline__ void assemble_diag(const CholArgs& A, const double* slab, const SlabGeom& G,
+                                              const double (*Part)[32 * PP], double* Dblk, int kk, int n,
+                                              bool with_part, int t0, int nthreads) {
+  const int c0 = 32 * kk;
+  // all loads of a thread are issued before the first use (clamped, branch-free addresses)
+  for (int e0 = t0; e0 < 1024; e0 += 8 * nthreads) {
+    double g[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      const int e = e0 + s * nthreads;
+      const int rl = (e >> 5) & 31, cl = e & 31;
+      const int row = min(c0 + rl, n - 1), col = min(c0 + cl, n - 1);
+      g[s] = (e < 1024) ? (A.dense ? A.dense[(size_t)row * A.ldd + col]
+                                   : __ldcg(slab + G.off(kk) + (size_t)(row - c0) * 32 + (col - c0)))
+                        : 0.0;
+    }
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      const int e = e0 + s * nthreads;
+      if (e >= 1024) continue;
+      const int rl = e >> 5, cl = e & 31;
+      double v = 0.0;
+      if (cl <= rl) {
+        const int row = c0 + rl, col = c0 + cl;
+        if (row < n && col < n) {
+          v = g[s] + ((A.dense && row == col) ? A.jitter : 0.0);
+          if (with_part) v -= (Part[0][rl * PP + cl] + Part[1][rl * PP + cl]) +
+                              (Part[2][rl * PP + cl] + Part[3][rl * PP + cl]);
+        } else {
+          v = (row == col) ? 1.0 : 0.0;
+        }
+      }
+      Dblk[rl * PS + cl] = v;
+    }
+  }
+}
+
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -375,36 +411,28 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
       }
       __syncthreads();   // also makes the Gram panel (written earlier) visible to the whole CTA
       BGP_STAMP(1);
-      for (int e = tid; e < 1024; e += NW * 32) {
-        const int rl = e >> 5, cl = e & 31;
-        double v = 0.0;
-        if (cl <= rl) {
-          const int row = c0 + rl, col = c0 + cl;
-          if (row < n && col < n) {
-            v = A.dense ? A.dense[(size_t)row * A.ldd + col] + (row == col ? A.jitter : 0.0)
-                        : slab[G.off(k) + (size_t)rl * 32 + cl];
-            if (k > 0) v -= (S.Part[0][rl * PP + cl] + S.Part[1][rl * PP + cl]) +
-                            (S.Part[2][rl * PP + cl] + S.Part[3][rl * PP + cl]);
-          } else {
-            v = (row == col) ? 1.0 : 0.0;
-          }
-        }
-        S.Dblk[rl * PS + cl] = v;
-      }
+      assemble_diag(A, slab, G, S.Part, S.Dblk, k, n, k > 0, tid, NW * 32);
       __syncthreads();
       BGP_STAMP(2);
+      // Warp 0 factors the diagonal block.  When K is not chunked the other warps do not wait for
+      // it: the trailing-update GEMM of their first round only needs previous panels, so they run
+      // it now and meet warp 0 at named barrier 2 right before the panel solve.
+      const bool overlap = nchunks <= 1 && NW > 1;
       if (warp == 0) {
         int f = warp_potrf32(S.Dblk, S.Lt, &S.Wd[0][0], lane, logdet, min(32, n - c0));
         if (f && lane == 0) S.fail = c0 + f;
         // L_kk -> slab (diag group rows of panel k)
         for (int e = lane; e < 1024; e += 32) slab[G.off(k) + e] = S.Lt[(e >> 5) * LS + (e & 31)];
         BGP_STAMP(3);
+        if (overlap) asm volatile("bar.sync 2, %0;" ::"r"(NW * 32) : "memory");
       } else if (A.dbg && warp == (A.dbg_tid >> 5)) {
         BGP_STAMP(3);
       }
-      __syncthreads();
+      if (!overlap) {
+        __syncthreads();
+        if (S.fail) break;
+      }
       BGP_STAMP(4);
-      if (S.fail) break;
 
       // ------------------------------------------------ phase 2: rows below the block, 8-row
       // tiles dealt evenly to the warps (up to four per warp and round)
@@ -413,12 +441,14 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
       const int T = n_main_t + 1 + n_aug_t;
       // warp w owns the contiguous tiles [w0, w0 + mine); every warp runs the same number of
       // rounds (barriers inside when K is chunked), each with at most four of its tiles
-      const int tq = T / NW, trm = T % NW;
-      const int mine = tq + (warp < trm ? 1 : 0);
-      const int w0 = warp * tq + min(warp, trm);
-      const int rounds = (tq + (trm ? 1 : 0) + 3) / 4;
-      const int per = rounds ? (mine + rounds - 1) / rounds : 0;
-      for (int rd = 0; rd < rounds; ++rd) {
+      const int nwk = overlap ? NW - 1 : NW;          // worker warps (warp 0 is busy when overlapping)
+      const int wrk = overlap ? warp - 1 : warp;
+      const int tq = T / nwk, trm = T % nwk;
+      const int mine = wrk < 0 ? 0 : tq + (wrk < trm ? 1 : 0);
+      const int w0 = wrk < 0 ? 0 : wrk * tq + min(wrk, trm);
+      const int rounds = max(1, (tq + (trm ? 1 : 0) + 3) / 4);
+      const int per = (mine + rounds - 1) / rounds;
+      for (int rd = 0; rd < rounds && wrk >= 0; ++rd) {
         const int first = w0 + rd * per;
         const int ntl = max(0, min(w0 + mine, first + per) - first);   // tiles of this warp and round
         TileSet TS;
@@ -453,6 +483,8 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
           }
         }
         BGP_STAMP_ADD(7, tph); tph = clock64();
+        if (overlap && rd == 0) asm volatile("bar.sync 2, %0;" ::"r"(NW * 32) : "memory");
+        if (S.fail) continue;
         double zpart = 0.0;
         switch (ntl) {
           case 4: finish_tiles<4>(acc, TS, A, S.Lt, &S.Wd[0][0], slab, G, k, n, npad, b, r, q, zpart); break;
@@ -467,7 +499,7 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
       BGP_STAMP(5);
       __syncthreads();
       BGP_STAMP(6);
-      (void)0;
+      if (S.fail) break;
     }
 
     // ------------------------------------------------------------------ epilogue

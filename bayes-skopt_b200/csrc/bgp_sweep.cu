@@ -1,7 +1,7 @@
 // K4: candidate sweep.  For one theta and a tile of candidates the CTA
 //   1. builds the cross-covariances k*(x_c, X) in shared memory (fused K1, never in HBM),
 //   2. computes the whitened vectors v = L^-1 k* as a triangular GEMM on DMMA.8x8x4, streaming
-//      L^-1 (the L^-T rows of the factor slab) from L2 with 32-byte loads,
+//      L^-1 (the L^-T rows of the factor slab) from L2 with 16-byte loads four steps ahead,
 //   3. reduces  var = k(x,x) - |v|^2  and  mean = v . z  (z = L^-1 y)  in the epilogue, so
 //      only 16 bytes per (theta, candidate) reach HBM.
 // Replaces skopt GaussianProcessRegressor.predict as called by bask/acquisition.py:121-129
@@ -83,53 +83,68 @@ __global__ void __launch_bounds__(SW_NW * 32, 1) sweep_kernel(SweepArgs A) {
 
   const double* slab = A.slabs + (size_t)s * G.doubles();
   const double* z = A.z + (size_t)s * n;
-  // balanced (zig-zag) assignment of row panels to warps
-  for (int base = 0; base < P; base += 2 * SW_NW) {
+  // Work unit = half a row panel of L^-1 (16 rows = two 8-row DMMA tiles); unit u needs the
+  // first 16(u+1) columns (triangular), so units are dealt to warps in zig-zag pairs (w, 2W-1-w):
+  // every warp gets the same number of 8-column steps whatever P is.
+  const int U = 2 * P;
+  for (int base = 0; base < U; base += 2 * SW_NW) {
     for (int side = 0; side < 2; ++side) {
-      const int j = side == 0 ? base + warp : base + 2 * SW_NW - 1 - warp;
-      if (j >= P) continue;
-      double acc[4][NT][2];
+      const int u = side == 0 ? base + warp : base + 2 * SW_NW - 1 - warp;
+      if (u >= U) continue;
+      const int j = u >> 1, hf = u & 1;
+      double acc[2][NT][2];
 #pragma unroll
-      for (int t = 0; t < 4; ++t)
+      for (int t = 0; t < 2; ++t)
 #pragma unroll
-        for (int u = 0; u < NT; ++u) acc[t][u][0] = acc[t][u][1] = 0.0;
-      const double* ap = slab + G.aug_base(j) + 4 * r + (size_t)32 * (2 * q);
-      const int steps = 4 * (j + 1);
-      double4 n0 = *reinterpret_cast<const double4*>(ap);
-      double4 n1 = *reinterpret_cast<const double4*>(ap + 32);
-      for (int st = 0; st < steps; ++st) {
-        const double4 a0 = n0, a1 = n1;
-        ap += 256;
-        if (st + 1 < steps) {
-          n0 = *reinterpret_cast<const double4*>(ap);
-          n1 = *reinterpret_cast<const double4*>(ap + 32);
-        }
-        double2 bv[NT];
+        for (int v = 0; v < NT; ++v) acc[t][v][0] = acc[t][v][1] = 0.0;
+      // A operand: (L^-1)[32j + 16hf + 2r + t][i] lives at aug_base(j) + 32 i + 16hf + 2r + t
+      const double* ap = slab + G.aug_base(j) + 16 * hf + 2 * r + (size_t)32 * (2 * q);
+      const int steps = 2 * (u + 1);
+      constexpr int PF = 4;
+      double2 ring[PF][2];
 #pragma unroll
-        for (int u = 0; u < NT; ++u)
-          bv[u] = *reinterpret_cast<const double2*>(Ks + (size_t)(8 * u + r) * kstride + 8 * st + 2 * q);
-#pragma unroll
-        for (int u = 0; u < NT; ++u) {
-          dmma(acc[0][u], a0.x, bv[u].x); dmma(acc[0][u], a1.x, bv[u].y);
-          dmma(acc[1][u], a0.y, bv[u].x); dmma(acc[1][u], a1.y, bv[u].y);
-          dmma(acc[2][u], a0.z, bv[u].x); dmma(acc[2][u], a1.z, bv[u].y);
-          dmma(acc[3][u], a0.w, bv[u].x); dmma(acc[3][u], a1.w, bv[u].y);
+      for (int s2 = 0; s2 < PF; ++s2) {
+        ring[s2][0] = ring[s2][1] = make_double2(0.0, 0.0);
+        if (s2 < steps) {
+          ring[s2][0] = *reinterpret_cast<const double2*>(ap + (size_t)256 * s2);
+          ring[s2][1] = *reinterpret_cast<const double2*>(ap + (size_t)256 * s2 + 32);
         }
       }
-      // epilogue of this row panel: rows 32j + 4r + t
-      const int row0 = 32 * j + 4 * r;
-      double zr[4];
+      for (int st0 = 0; st0 < steps; st0 += PF) {
 #pragma unroll
-      for (int t = 0; t < 4; ++t) zr[t] = (row0 + t < n) ? z[row0 + t] : 0.0;
+        for (int s2 = 0; s2 < PF; ++s2) {
+          const int st = st0 + s2;
+          if (st < steps) {
+            const double2 a0 = ring[s2][0], a1 = ring[s2][1];   // k = 8st+2q (rows 2r, 2r+1), k+1
+            if (st + PF < steps) {
+              ring[s2][0] = *reinterpret_cast<const double2*>(ap + (size_t)256 * (st + PF));
+              ring[s2][1] = *reinterpret_cast<const double2*>(ap + (size_t)256 * (st + PF) + 32);
+            }
+            double2 bv[NT];
 #pragma unroll
-      for (int u = 0; u < NT; ++u) {
+            for (int v = 0; v < NT; ++v)
+              bv[v] = *reinterpret_cast<const double2*>(Ks + (size_t)(8 * v + r) * kstride + 8 * st + 2 * q);
+#pragma unroll
+            for (int v = 0; v < NT; ++v) { dmma(acc[0][v], a0.x, bv[v].x); dmma(acc[1][v], a0.y, bv[v].x); }
+#pragma unroll
+            for (int v = 0; v < NT; ++v) { dmma(acc[0][v], a1.x, bv[v].y); dmma(acc[1][v], a1.y, bv[v].y); }
+          }
+        }
+      }
+      // epilogue of this unit: rows 32j + 16hf + 2r + t
+      const int row0 = 32 * j + 16 * hf + 2 * r;
+      double zr[2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) zr[t] = (row0 + t < n) ? z[row0 + t] : 0.0;
+#pragma unroll
+      for (int v = 0; v < NT; ++v) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           double pv = 0.0, pm = 0.0;
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            pv = fma(acc[t][u][e], acc[t][u][e], pv);
-            pm = fma(acc[t][u][e], zr[t], pm);
+          for (int t = 0; t < 2; ++t) {
+            pv = fma(acc[t][v][e], acc[t][v][e], pv);
+            pm = fma(acc[t][v][e], zr[t], pm);
           }
 #pragma unroll
           for (int o = 4; o < 32; o <<= 1) {
@@ -137,40 +152,37 @@ __global__ void __launch_bounds__(SW_NW * 32, 1) sweep_kernel(SweepArgs A) {
             pm += __shfl_xor_sync(0xffffffffu, pm, o);
           }
           if (r == 0) {
-            S.sums[warp][8 * u + 2 * q + e][0] += pv;
-            S.sums[warp][8 * u + 2 * q + e][1] += pm;
+            S.sums[warp][8 * v + 2 * q + e][0] += pv;
+            S.sums[warp][8 * v + 2 * q + e][1] += pm;
           }
         }
       }
       if (A.R > 0) {
         for (int rr = 0; rr < A.R; ++rr) {
           const double* ze = A.zextra + ((size_t)s * A.R + rr) * n;
-          double ez[4];
+          double ez[2];
 #pragma unroll
-          for (int t = 0; t < 4; ++t) ez[t] = (row0 + t < n) ? ze[row0 + t] : 0.0;
+          for (int t = 0; t < 2; ++t) ez[t] = (row0 + t < n) ? ze[row0 + t] : 0.0;
 #pragma unroll
-          for (int u = 0; u < NT; ++u)
+          for (int v = 0; v < NT; ++v)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              double pe = 0.0;
-#pragma unroll
-              for (int t = 0; t < 4; ++t) pe = fma(acc[t][u][e], ez[t], pe);
+              double pe = fma(acc[0][v][e], ez[0], acc[1][v][e] * ez[1]);
 #pragma unroll
               for (int o = 4; o < 32; o <<= 1) pe += __shfl_xor_sync(0xffffffffu, pe, o);
-              if (r == 0) atomicAdd(&dotx[rr * NC + 8 * u + 2 * q + e], pe);
+              if (r == 0) atomicAdd(&dotx[rr * NC + 8 * v + 2 * q + e], pe);
             }
         }
       }
       if (A.v_out) {
 #pragma unroll
-        for (int u = 0; u < NT; ++u)
+        for (int v = 0; v < NT; ++v)
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const int ci = c0 + 8 * u + 2 * q + e;
+            const int ci = c0 + 8 * v + 2 * q + e;
             if (ci < A.m) {
               double* dst = A.v_out + ((size_t)s * A.m + ci) * A.v_ld + row0;
-              *reinterpret_cast<double4*>(dst) =
-                  make_double4(acc[0][u][e], acc[1][u][e], acc[2][u][e], acc[3][u][e]);
+              *reinterpret_cast<double2*>(dst) = make_double2(acc[0][v][e], acc[1][v][e]);
             }
           }
       }
