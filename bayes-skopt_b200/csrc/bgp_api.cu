@@ -234,7 +234,7 @@ static int logprob_impl(bgp_handle_t h, const double* theta_dev, int batch, cons
     A.priors = h->have_priors ? h->priors.as<bgp_prior_t>() : nullptr; A.n_priors = h->n_priors;
     A.n = h->n; A.d = h->d; A.batch = nb; A.aug = 0; A.slab_per_block = 0;
     A.dbg = h->dbg; A.dbg_tid = h->dbg_tid;
-    CUDA_TRY(bgp::launch_chol(A, nb, st));
+    CUDA_TRY(bgp::launch_chol(A, nb, h->sms, st));
   }
   return 0;
 }
@@ -280,7 +280,7 @@ int bgp_factorize_batched(bgp_handle_t h, const double* theta_dev, int S, double
   A.theta = theta_dev; A.lml = lml_dev; A.info = info_dev; A.slabs = slabs_dev; A.z_out = z_dev;
   A.prog = h->prog.as<DevProgram>(); A.fixed_ls = h->fixed_ls.as<double>();
   A.n = h->n; A.d = h->d; A.batch = S; A.aug = 1; A.slab_per_block = 0;
-  CUDA_TRY(bgp::launch_chol(A, S, st));
+  CUDA_TRY(bgp::launch_chol(A, S, h->sms, st));
   return 0;
 }
 
@@ -432,7 +432,7 @@ int bgp_dense_cholesky(bgp_handle_t h, const double* a_dev, int m, int64_t lda, 
   std::memset(&A, 0, sizeof(A));
   A.slabs = slab_dev; A.info = info_dev; A.n = m; A.d = 1; A.batch = 1; A.aug = 0; A.slab_per_block = 0;
   A.dense = a_dev; A.ldd = lda; A.jitter = jitter;
-  CUDA_TRY(bgp::launch_chol(A, 1, (cudaStream_t)stream));
+  CUDA_TRY(bgp::launch_chol(A, 1, h->sms, (cudaStream_t)stream));
   if (h->have_data) CUDA_TRY(bgp::prepare_chol(h->n));
   return 0;
 }

@@ -338,11 +338,22 @@ __device__ __forceinline__ void assemble_diag(const CholArgs& A, const double* s
   }
 }
 
-template <int NW>
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+// CS = CTAs per theta.  With CS > 1 (used when the batch leaves SMs idle: CS * batch <= #SMs) a
+// thread-block cluster of CS CTAs shares one matrix: all run the short serial chain (diagonal
+// update, potrf) redundantly -- it is deterministic, so no exchange is needed -- and split the
+// row tiles of the trailing update / panel solve; a cluster barrier per panel publishes the rows
+// each of them wrote to the (L2-resident) slab.
+template <int NW, int CS>
 __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CholSmem<NW>& S = *reinterpret_cast<CholSmem<NW>*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int crank = 0;
+  if (CS > 1) asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
   const int r = lane >> 2, q = lane & 3;
   const int n = A.n, d = A.d;
   const SlabGeom G = SlabGeom::make(n, A.aug != 0);
@@ -360,9 +371,9 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
   __syncthreads();
   const DevProgram& PR = S.prog;
 
-  for (int b = blockIdx.x; b < A.batch; b += gridDim.x) {
+  for (int b = blockIdx.x / CS; b < A.batch; b += gridDim.x / CS) {
     const double* theta = A.theta + (size_t)b * PR.n_theta;
-    double* slab = A.slabs + (size_t)(A.slab_per_block ? blockIdx.x : b) * G.doubles();
+    double* slab = A.slabs + (size_t)(A.slab_per_block ? blockIdx.x / CS : b) * G.doubles();
     if (tid == 0) S.fail = 0;
     double logdet = 0.0, zz = 0.0;   // meaningful in warp 0 / z-row owners
     __syncthreads();
@@ -422,7 +433,8 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
         int f = warp_potrf32(S.Dblk, S.Lt, &S.Wd[0][0], lane, logdet, min(32, n - c0));
         if (f && lane == 0) S.fail = c0 + f;
         // L_kk -> slab (diag group rows of panel k)
-        for (int e = lane; e < 1024; e += 32) slab[G.off(k) + e] = S.Lt[(e >> 5) * LS + (e & 31)];
+        if (crank == 0)
+          for (int e = lane; e < 1024; e += 32) slab[G.off(k) + e] = S.Lt[(e >> 5) * LS + (e & 31)];
         BGP_STAMP(3);
         if (overlap) asm volatile("bar.sync 2, %0;" ::"r"(NW * 32) : "memory");
       } else if (A.dbg && warp == (A.dbg_tid >> 5)) {
@@ -436,9 +448,15 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
 
       // ------------------------------------------------ phase 2: rows below the block, 8-row
       // tiles dealt evenly to the warps (up to four per warp and round)
-      const int n_main_t = 4 * (P - 1 - k);
-      const int n_aug_t = A.aug ? 4 * (k + 1) : 0;
-      const int T = n_main_t + 1 + n_aug_t;
+      // 32-row groups below the diagonal and identity-row groups; with CS == 2 groups alternate
+      // between the two CTAs of the cluster and the y tile belongs to rank 0
+      const int nmg = P - 1 - k, nag = A.aug ? k + 1 : 0;
+      const int my_mg = (nmg - crank + CS - 1) / CS;                 // groups crank, crank + CS, ...
+      const int a0 = ((crank - nmg) % CS + CS) % CS;                  // continue the deal over identity groups
+      const int my_ag = nag > a0 ? (nag - a0 + CS - 1) / CS : 0;
+      const int has_z = (CS == 1 || crank == 0) ? 1 : 0;
+      const int n_main_t = 4 * my_mg;
+      const int T = n_main_t + has_z + 4 * my_ag;
       // warp w owns the contiguous tiles [w0, w0 + mine); every warp runs the same number of
       // rounds (barriers inside when K is chunked), each with at most four of its tiles
       const int nwk = overlap ? NW - 1 : NW;          // worker warps (warp 0 is busy when overlapping)
@@ -457,9 +475,16 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
           const int ti = first + t;
           TS.rb[t] = c0; TS.kind[t] = 3; TS.js[t] = 0;   // kind 3: padding slot of the tile set
           if (t < ntl) {
-            if (ti < n_main_t) { TS.rb[t] = 32 * (k + 1) + 8 * ti; TS.kind[t] = 0; }
-            else if (ti == n_main_t) { TS.rb[t] = G.Rz; TS.kind[t] = 1; }
-            else { const int a = ti - n_main_t - 1; TS.rb[t] = G.Ra + 8 * a; TS.kind[t] = 2; TS.js[t] = a >> 2; }
+            if (ti < n_main_t) {
+              const int g = CS * (ti >> 2) + crank;
+              TS.rb[t] = 32 * (k + 1) + 32 * g + 8 * (ti & 3); TS.kind[t] = 0;
+            } else if (has_z && ti == n_main_t) {
+              TS.rb[t] = G.Rz; TS.kind[t] = 1;
+            } else {
+              const int l2 = ti - n_main_t - has_z;
+              const int a = a0 + CS * (l2 >> 2);
+              TS.rb[t] = G.Ra + 32 * a + 8 * (l2 & 3); TS.kind[t] = 2; TS.js[t] = a;
+            }
           }
         }
         long long tph = clock64();
@@ -497,7 +522,7 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
         BGP_STAMP_ADD(8, tph);
       }
       BGP_STAMP(5);
-      __syncthreads();
+      if (CS > 1) cluster_barrier(); else __syncthreads();
       BGP_STAMP(6);
       if (S.fail) break;
     }
@@ -507,7 +532,7 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
     if (warp == 0) logdet = warp_sum(logdet);
     if (lane == 0) S.red[warp] = zz;
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0 && crank == 0) {
       double ztz = 0.0;
       for (int w = 0; w < NW; ++w) ztz += S.red[w];
       double lml, lp;
@@ -538,20 +563,50 @@ static size_t chol_smem_bytes(int n) {
   return base + sizeof(double) * (size_t)32 * (32 * kch + 8);
 }
 
+// largest portable cluster size that still fits the batch on the chip
+static int pick_cluster(int n, int grid_thetas, int sms) {
+  if (pick_nw(n) != 8) return 1;
+  for (int cs = 8; cs > 1; cs >>= 1)
+    if (cs * grid_thetas <= sms) return cs;
+  return 1;
+}
+
+template <int CS>
+static cudaError_t launch_cluster(const CholArgs& A, int grid, size_t smem, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(CS * grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, chol_lml_kernel<8, CS>, A);
+}
+
 // opt-in to the large dynamic shared-memory carve-out (must happen outside stream capture)
 cudaError_t prepare_chol(int n) {
   const size_t smem = chol_smem_bytes(n);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  return pick_nw(n) == 4
-             ? cudaFuncSetAttribute(chol_lml_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-             : cudaFuncSetAttribute(chol_lml_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (pick_nw(n) == 4)
+    return cudaFuncSetAttribute(chol_lml_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(chol_lml_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(chol_lml_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(chol_lml_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(chol_lml_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  return e;
 }
 
-cudaError_t launch_chol(const CholArgs& A, int grid, cudaStream_t stream) {
+cudaError_t launch_chol(const CholArgs& A, int grid, int sms, cudaStream_t stream) {
   const size_t smem = chol_smem_bytes(A.n);
-  if (pick_nw(A.n) == 4) chol_lml_kernel<4><<<grid, 128, smem, stream>>>(A);
-  else chol_lml_kernel<8><<<grid, 256, smem, stream>>>(A);
-  return cudaGetLastError();
+  if (pick_nw(A.n) == 4) {
+    chol_lml_kernel<4, 1><<<grid, 128, smem, stream>>>(A);
+    return cudaGetLastError();
+  }
+  switch (pick_cluster(A.n, grid, sms)) {
+    case 8: return launch_cluster<8>(A, grid, smem, stream);
+    case 4: return launch_cluster<4>(A, grid, smem, stream);
+    case 2: return launch_cluster<2>(A, grid, smem, stream);
+    default: chol_lml_kernel<8, 1><<<grid, 256, smem, stream>>>(A); return cudaGetLastError();
+  }
 }
 
 }  // namespace bgp

@@ -32,7 +32,7 @@ struct CholArgs {
   int dbg_tid;           // thread that records them
 };
 cudaError_t prepare_chol(int n);
-cudaError_t launch_chol(const CholArgs& A, int grid, cudaStream_t stream);
+cudaError_t launch_chol(const CholArgs& A, int grid, int sms, cudaStream_t stream);
 
 struct GramArgs {
   const double* X;       // n x d
