@@ -347,6 +347,8 @@ __device__ __forceinline__ void cluster_barrier() {
 // update, potrf) redundantly -- it is deterministic, so no exchange is needed -- and split the
 // row tiles of the trailing update / panel solve; a cluster barrier per panel publishes the rows
 // each of them wrote to the (L2-resident) slab.
+constexpr int MAXT = 3;   // row tiles per warp and round
+
 template <int NW, int CS>
 __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -464,7 +466,7 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
       const int tq = T / nwk, trm = T % nwk;
       const int mine = wrk < 0 ? 0 : tq + (wrk < trm ? 1 : 0);
       const int w0 = wrk < 0 ? 0 : wrk * tq + min(wrk, trm);
-      const int rounds = max(1, (tq + (trm ? 1 : 0) + 3) / 4);
+      const int rounds = max(1, (tq + (trm ? 1 : 0) + MAXT - 1) / MAXT);
       const int per = (mine + rounds - 1) / rounds;
       for (int rd = 0; rd < rounds && wrk >= 0; ++rd) {
         const int first = w0 + rd * per;
@@ -500,7 +502,6 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
             __syncthreads();
           }
           switch (ntl) {
-            case 4: k_chunk<4>(acc, TS, slab, G, Bs, bstride, j0, kc, r, q); break;
             case 3: k_chunk<3>(acc, TS, slab, G, Bs, bstride, j0, kc, r, q); break;
             case 2: k_chunk<2>(acc, TS, slab, G, Bs, bstride, j0, kc, r, q); break;
             case 1: k_chunk<1>(acc, TS, slab, G, Bs, bstride, j0, kc, r, q); break;
@@ -512,7 +513,6 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
         if (S.fail) continue;
         double zpart = 0.0;
         switch (ntl) {
-          case 4: finish_tiles<4>(acc, TS, A, S.Lt, &S.Wd[0][0], slab, G, k, n, npad, b, r, q, zpart); break;
           case 3: finish_tiles<3>(acc, TS, A, S.Lt, &S.Wd[0][0], slab, G, k, n, npad, b, r, q, zpart); break;
           case 2: finish_tiles<2>(acc, TS, A, S.Lt, &S.Wd[0][0], slab, G, k, n, npad, b, r, q, zpart); break;
           case 1: finish_tiles<1>(acc, TS, A, S.Lt, &S.Wd[0][0], slab, G, k, n, npad, b, r, q, zpart); break;
