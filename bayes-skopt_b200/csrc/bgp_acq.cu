@@ -10,7 +10,7 @@ namespace bgp {
 
 constexpr int MES_PTS = 192;      // trial points evaluated per refinement round (3 x 64)
 constexpr int MES_CH = 512;       // candidates per block in the quantile search
-constexpr int MES_NEWTON = 10;
+constexpr int MES_NEWTON = 6;        // quadratic from a 1/63^2 bracket: converged after 3, 6 for margin
 constexpr int ST = 8;             // doubles of per-theta statistics
 constexpr int MS = 16;            // doubles of per-theta MES search state
 
@@ -284,8 +284,11 @@ __global__ void mes_epilogue_kernel(const double* __restrict__ mu, const double*
     const double gam = (maxv[k] - mean) / b;
     double term;
     if (gam > 0.0) {
-      const double e = 0.5 * erfc(gam * 0.7071067811865476);
-      term = gam * norm_pdf(gam) / (2.0 * (1.0 - e)) - log1p(-e);
+      // one exp shared by phi and Phi: erfc(t) = erfcx(t) exp(-t^2), phi = exp(-t^2) / sqrt(2 pi)
+      const double t = gam * 0.7071067811865476;
+      const double E = exp(-t * t);
+      const double e = 0.5 * erfcx(t) * E;
+      term = gam * 0.3989422804014327 * E / (2.0 * (1.0 - e)) - log1p(-e);
     } else {
       const double t = -gam * 0.7071067811865476;
       if (t < 26.0) {

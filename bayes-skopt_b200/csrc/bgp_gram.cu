@@ -34,13 +34,19 @@ __global__ void __launch_bounds__(256) scale_x_kernel(GramArgs A) {
   }
 }
 
-// CTA (panel k, theta b): rows [32k, n) x 32 columns of the lower triangle.  A warp takes
-// eight rows per iteration (eight independent sqrt/exp chains), lanes are the 32 columns.
+// CTA (64-row chunk of panel k, theta b): 64 x 32 entries of the lower triangle.  A warp takes
+// eight rows (eight independent sqrt/exp chains), lanes are the 32 columns.  Chunks of all panels
+// are enumerated along blockIdx.x so that every CTA has the same amount of work.
+constexpr int GRAM_ROWS = 64;
+__host__ __device__ inline int gram_chunks(int n, int k) { return (n - 32 * k + GRAM_ROWS - 1) / GRAM_ROWS; }
+
 __global__ void __launch_bounds__(256) gram_kernel(GramArgs A) {
   __shared__ DevProgram PR;
   __shared__ ThetaParams TP;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.y, k = blockIdx.x, n = A.n, d = A.d;
+  const int b = blockIdx.y, n = A.n, d = A.d;
+  int k = 0, chunk = blockIdx.x;
+  while (chunk >= gram_chunks(n, k)) { chunk -= gram_chunks(n, k); ++k; }
   {
     const int* src = reinterpret_cast<const int*>(A.prog);
     int* dst = reinterpret_cast<int*>(&PR);
@@ -55,7 +61,8 @@ __global__ void __launch_bounds__(256) gram_kernel(GramArgs A) {
   double* base = A.slabs + (size_t)b * G.doubles() + G.off(k);
   constexpr int RB = 8;
   const int c0 = 32 * k, col = c0 + lane;
-  for (int r0 = c0 + RB * warp; r0 < n; r0 += RB * 8) {
+  {
+    const int r0 = c0 + GRAM_ROWS * chunk + RB * warp;
     if (PR.fast_kind) {
       double r2[RB];
 #pragma unroll
@@ -117,7 +124,9 @@ cudaError_t launch_gram(const GramArgs& A, cudaStream_t stream) {
   const int per_theta = (int)((gram_xt_doubles(A.n, A.d, 1) * 4 + 255) / 256);
   dim3 gs(per_theta < 1 ? 1 : (per_theta > 32 ? 32 : per_theta), A.batch);
   scale_x_kernel<<<gs, 256, 0, stream>>>(A);
-  dim3 gg(P, A.batch);
+  int chunks = 0;
+  for (int k = 0; k < P; ++k) chunks += gram_chunks(A.n, k);
+  dim3 gg(chunks, A.batch);
   gram_kernel<<<gg, 256, 0, stream>>>(A);
   return cudaGetLastError();
 }

@@ -17,6 +17,9 @@ __all__ = ["make_roundflat", "RoundFlatPrior", "HalfNormalSqrtPrior", "InvGammaP
            "NormalPrior", "as_device_priors"]
 
 
+_NORM_CACHE = {}
+
+
 def make_roundflat(lower_bound=0.1, upper_bound=0.6, lower_steepness=2.0, upper_steepness=8.0,
                    integration_bounds=(0.0, 10.0)):
     """Round-flat log-density on the ORIGINAL scale (bask/priors.py:7-57): roughly flat inside
@@ -25,8 +28,12 @@ def make_roundflat(lower_bound=0.1, upper_bound=0.6, lower_steepness=2.0, upper_
         return -2 * ((x / lower_bound) ** (-2 * lower_steepness)
                      + (x / upper_bound) ** (2 * upper_steepness))
 
-    with np.errstate(divide="ignore", over="ignore"):
-        value = quad(lambda x: np.exp(roundflat(x)), integration_bounds[0], integration_bounds[1])[0]
+    key = (lower_bound, upper_bound, lower_steepness, upper_steepness, tuple(integration_bounds))
+    if key not in _NORM_CACHE:   # the reference re-integrates on every guess_priors call (~0.5 ms)
+        with np.errstate(divide="ignore", over="ignore"):
+            _NORM_CACHE[key] = quad(lambda x: np.exp(roundflat(x)), integration_bounds[0],
+                                    integration_bounds[1])[0]
+    value = _NORM_CACHE[key]
 
     def prior(x):
         return roundflat(x) - np.log(value)
