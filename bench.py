@@ -64,17 +64,20 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.time()] + [c.strip() for c in line.split(",")])
 
     def __exit__(self, *a):
         if self.proc:
             self.proc.terminate()
             self.t.join(timeout=2)
 
-    def summary(self):
+    def summary(self, t0=None, t1=None):
+        """median SM clock / throttle reasons of the samples that arrived inside [t0, t1] (the timed
+        region); nvidia-smi needs ~0.2 s to start, so the sampler is started before the warm-up"""
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r[1:] for r in self.rows if t0 is None or (t0 - 0.02 <= r[0] <= t1 + 0.12)]
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for nm, v in zip(names, r[5:9]):
@@ -139,16 +142,20 @@ def run_reference(args):
         return
     w = W.config3()
     times, detail = [], None
+    # bounded sample per step, sized so that the whole run takes about 75 s of CPU time
+    budget = 75.0 / max(1, args.warmup + args.steps)
+    n_lml = int(min(256, max(16, budget * 0.4 / 0.006)))
+    n_cand = int(min(2000, max(200, budget * 0.5 / 0.00045)))
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        cyc, detail = cpu_reference_cycle(w, lml_evals=192, sweep_thetas=1, sweep_cands=1500, seed=i)
+        cyc, detail = cpu_reference_cycle(w, lml_evals=n_lml, sweep_thetas=1, sweep_cands=n_cand, seed=i)
         if i >= args.warmup:
             times.append(cyc)
         detail["sample_wall_s"] = time.perf_counter() - t0
     cyc = float(np.mean(times))
     value = w.n_logprob_evals / cyc
-    sample = ("per step: 192 log-posterior evals + 1 theta-setter + predict/MES over 1500 candidates at n=500, "
-              "extrapolated linearly to 1536 evals + 10 thetas x 10000 candidates")
+    sample = (f"per step: {n_lml} log-posterior evals + 1 theta-setter + predict/MES over {n_cand} candidates at "
+              "n=500, extrapolated linearly to 1536 evals + 10 thetas x 10000 candidates")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * cyc, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -234,20 +241,23 @@ def run_b200(args):
         out, _, _, _ = e.acq(_lib.ACQ_MES, mu, sd, gumbel32=g32_dev)
         return e.argmax(out)
 
-    for i in range(args.warmup):
-        device_cycle(100 + i)
-    barrier()
-    l0 = e.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
+        for i in range(args.warmup):
+            device_cycle(100 + i)
+        barrier()
+        l0 = e.launches
+        t_begin = time.time()
         ev0.record(e.stream)
         for i in range(args.steps):
             device_cycle(200 + i)
         ev1.record(e.stream)
         barrier()
+        t_end = time.time()
+        time.sleep(0.15)
     dev_ms = ev0.elapsed_time(ev1) / args.steps
     launches = (e.launches - l0) // max(args.steps, 1)
-    clocks = clk.summary()
+    clocks = clk.summary(t_begin, t_end)
 
     # ---------------- end to end through the public API (host buffers in, host results out)
     def e2e_cycle(seed):
@@ -287,6 +297,10 @@ def run_b200(args):
     chol_ms = k0.elapsed_time(k1) / reps
     peaks = json.load(open(os.path.join(REPO, "profiles", "fp64_peaks_r01.json")))
     peak_tf = float(peaks["dmma_tflops_w8"])
+    try:    # DRAM bytes per launch of the factorisation kernel from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(REPO, "profiles", "ncu_traffic_r01.json")))["chol_lml_kernel"]
+    except Exception:
+        traffic = None
     chol_tf = nb * flops_lml(w.n, w.d) / (chol_ms * 1e-3) / 1e12
     # sweep kernel
     th = e.to_dev(gp.chain_[picks])
@@ -321,9 +335,11 @@ def run_b200(args):
                 "e2e": {"value": evals / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches),
-                "roofline": {"kernel": "chol_lml_kernel<16> (Gram+Cholesky+LML, 64 thetas, n=500)",
+                "roofline": {"kernel": "scale_x + gram_kernel + chol_lml_kernel<8,2> (K1+K2: Gram, Cholesky, LML; 64 thetas, n=500)",
                              "bound": "tensor", "achieved": chol_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                             "frac": chol_tf / peak_tf, "traffic": None,
+                             "frac": chol_tf / peak_tf, "traffic": traffic,
+                             "traffic_note": "dram read+write bytes per launch from one ncu --set full capture (cold L2: ncu "
+                                             "flushes caches, in the pipeline the slabs are L2 hits); algorithmic bytes ~30 KB",
                              "peak_source": "measured FP64 DMMA.8x8x4 issue peak on this pool (profiles/fp64_peaks_r01.json; "
                                             "MEASURED_PEAKS.json has no FP64 entry; cuBLAS DGEMM 8192^3 = 35.5)",
                              "launch_ms": chol_ms},
@@ -345,8 +361,8 @@ def run_b200(args):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
