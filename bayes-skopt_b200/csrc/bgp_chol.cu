@@ -26,7 +26,6 @@ struct CholSmem {
   double Dblk[32 * PS];              // diagonal block being factored
   double Lt[32 * LS];                // factored block L_kk, DMMA-friendly stride
   double Wd[4][8 * 8];               // inverses of its four 8x8 diagonal sub-blocks
-  double Part[4][32 * PP];           // K-split partial sums of the diagonal update
   double red[NW];
   int fail;
 };
@@ -59,71 +58,112 @@ __device__ __forceinline__ double log_prior(const bgp_prior_t* pr, int n, const 
 }
 
 // ---- warp-level Cholesky of the 32x32 diagonal block + inverses of its 8x8 diagonal blocks --
-// Lane i owns row i.  Columns are processed in blocks of eight held in registers: a rolled
-// left-looking update from the previous column blocks (shared memory), then an unrolled
-// in-register factorisation of the eight columns with shuffles, so the per-column critical
-// path is shuffle -> rsqrt -> scale -> shuffle -> fma.  The panel solve only needs the four
-// 8x8 inverses (block forward substitution on DMMA), computed at the end by all lanes at once.
+// Right-looking over 8-column blocks with the block held in DMMA accumulator layout (lane (r,q)
+// owns [8t+r][8u+2q..2q+1] of sub-tile (t,u)):
+//   1. every lane reads the current 8x8 diagonal sub-block from shared memory (broadcast) and
+//      factors it redundantly in registers -- no shuffles on the rsqrt -> scale -> fma chain;
+//   2. lane c (mod 8) derives column c of W = L_bb^-1 from its register copy;
+//   3. the sub-tiles below become X = C W^T and the trailing sub-tiles C -= X X^T on DMMA; the
+//      accumulator layout doubles as the A and the B operand (k-permutation), so nothing moves.
+// The panel solve only needs L_kk (DMMA-friendly copy Lt) and the four 8x8 inverses Wd.
 // Returns 0 or failing local column + 1 (LAPACK dpotrf: pivot <= 0 or NaN).
-__device__ __noinline__ int warp_potrf32(double* __restrict__ D, double* __restrict__ Lt,
-                                         double* __restrict__ Wd, int lane, double& logdet, int ncols_real) {
+__device__ __forceinline__ int warp_potrf32(double* __restrict__ D, double* __restrict__ Lt,
+                                         double* __restrict__ Wd, int lane, double& logdet, int ncols_real,
+                                            long long* ts = nullptr) {
+  const int r = lane >> 2, q = lane & 3, ci = lane & 7;
+#define POTRF_TS(i) do { if (ts && lane == 0) ts[i] = clock64(); } while (0)
+  POTRF_TS(0);
   int fail = 0;
-  double* __restrict__ myrow = D + lane * PS;
-  double my_inv = 1.0, w[8];
-  for (int b = 0; b < 4; ++b) {
+  double C[4][4][2];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) w[c] = myrow[8 * b + c];
-    for (int k = 0; k < 8 * b; ++k) {
-      const double lik = myrow[k];
+  for (int t = 0; t < 4; ++t)
 #pragma unroll
-      for (int c = 0; c < 8; ++c) w[c] = fma(-lik, D[(8 * b + c) * PS + k], w[c]);
+    for (int u = 0; u <= t; ++u) {
+      C[t][u][0] = D[(8 * t + r) * PS + 8 * u + 2 * q];
+      C[t][u][1] = D[(8 * t + r) * PS + 8 * u + 2 * q + 1];
     }
+  double invprod = 1.0;   // lane c < 8: product of 1/L_jj over its columns j = c (mod 8)
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    if (b > 0) {
+      D[(8 * b + r) * PS + 8 * b + 2 * q] = C[b][b][0];
+      D[(8 * b + r) * PS + 8 * b + 2 * q + 1] = C[b][b][1];
+      __syncwarp();
+    }
+    POTRF_TS(1 + 6 * b);
+    double a[8][8], inv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) a[i][j] = D[(8 * b + i) * PS + 8 * b + j];
+    POTRF_TS(2 + 6 * b);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      const int j = 8 * b + c;
-      double ajj = __shfl_sync(0xffffffffu, w[c], j);
-      if (!(ajj > 0.0)) { if (!fail) fail = j + 1; ajj = 1.0; }
-      const double inv = rsqrt(ajj);
-      const double lij = lane > j ? w[c] * inv : (lane == j ? ajj * inv : 0.0);
-      if (lane == j) my_inv = inv;
-      w[c] = lij;
+      double ajj = a[c][c];
+      if (!(ajj > 0.0)) { if (!fail) fail = 8 * b + c + 1; ajj = 1.0; }
+      inv[c] = rsqrt(ajj);
+      a[c][c] = ajj * inv[c];
 #pragma unroll
-      for (int c2 = c + 1; c2 < 8; ++c2) {
-        const double lkj = __shfl_sync(0xffffffffu, lij, 8 * b + c2);
-        w[c2] = fma(-lij, lkj, w[c2]);
-      }
+      for (int i = c + 1; i < 8; ++i) a[i][c] *= inv[c];
+#pragma unroll
+      for (int j = c + 1; j < 8; ++j)
+#pragma unroll
+        for (int i = j; i < 8; ++i) a[i][j] = fma(-a[i][c], a[j][c], a[i][j]);
+      if (lane == c && 8 * b + c < ncols_real) invprod *= inv[c];
     }
+    POTRF_TS(3 + 6 * b);
+    // column ci of W_bb by forward substitution on the register copy
+    double x[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) myrow[8 * b + c] = w[c];
+    for (int i = 0; i < 8; ++i) {
+      double sacc = (i == ci) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < i; ++k) sacc = fma(-a[i][k], x[k], sacc);
+      x[i] = (i >= ci) ? sacc * inv[i] : 0.0;
+    }
+    POTRF_TS(4 + 6 * b);
+    if (lane < 8) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) Wd[b * 64 + i * 8 + ci] = x[i];
+    }
     __syncwarp();
-  }
-  if (lane < ncols_real) logdet -= log(my_inv);
-  // after the loop w[] holds this lane's entries of column block 3; reload the diagonal block
-  // row of this lane's own 8x8 sub-block: lanes 8g..8g+7 hold L_gg row-wise
-  const int g = lane >> 3, ci = lane & 7;
+    POTRF_TS(5 + 6 * b);
+    {
+      // X = C W^T for the sub-tiles of this block column; for the diagonal sub-tile itself this
+      // reproduces L_bb (C_bb = L_bb L_bb^T, only the lower part of C_bb enters the lower part
+      // of the product) in accumulator layout, which is what the Lt copy is written from
+      const double2 wv = *reinterpret_cast<const double2*>(Wd + b * 64 + r * 8 + 2 * q);
 #pragma unroll
-  for (int c = 0; c < 8; ++c) w[c] = myrow[8 * g + c];
-  // column ci of W_gg = L_gg^-1 by forward substitution; L_gg[i][k] lives in lane 8g+i, w[k]
-  double x[8];
+      for (int t = b; t < 4; ++t) {
+        double o[2] = {0.0, 0.0};
+        dmma(o, C[t][b][0], wv.x);
+        dmma(o, C[t][b][1], wv.y);
+        C[t][b][0] = o[0]; C[t][b][1] = o[1];
+      }
+      if (2 * q > r) C[b][b][0] = 0.0;
+      if (2 * q + 1 > r) C[b][b][1] = 0.0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    double sacc = (i == ci) ? 1.0 : 0.0;
+      for (int u = b + 1; u < 4; ++u)
 #pragma unroll
-    for (int k = 0; k < i; ++k) {
-      const double lik = __shfl_sync(0xffffffffu, w[k], i, 8);
-      sacc = fma(-lik, x[k], sacc);
+        for (int t = u; t < 4; ++t) {
+          dmma(C[t][u], C[t][b][0], -C[u][b][0]);
+          dmma(C[t][u], C[t][b][1], -C[u][b][1]);
+        }
     }
-    const double dinv = __shfl_sync(0xffffffffu, my_inv, i, 8);
-    x[i] = (i >= ci) ? sacc * dinv : 0.0;
   }
+  POTRF_TS(25);
+  if (lane < 8) logdet -= log(invprod);
+  POTRF_TS(26);
+  // DMMA-friendly copy of L_kk, zeros above the diagonal
 #pragma unroll
-  for (int i = 0; i < 8; ++i) Wd[g * 64 + i * 8 + ci] = x[i];
-  // DMMA-friendly copy of L_kk (zeros above the diagonal)
-  for (int e = lane; e < 1024; e += 32) {
-    const int rr = e >> 5, cc = e & 31;
-    Lt[rr * LS + cc] = cc <= rr ? D[rr * PS + cc] : 0.0;
-  }
+  for (int t = 0; t < 4; ++t)
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      *reinterpret_cast<double2*>(Lt + (8 * t + r) * LS + 8 * u + 2 * q) =
+          u <= t ? make_double2(C[t][u][0], C[t][u][1]) : make_double2(0.0, 0.0);
   __syncwarp();
+  POTRF_TS(27);
+#undef POTRF_TS
   return fail;
 }
 
@@ -141,6 +181,8 @@ __device__ __forceinline__ void stage_block_row(const double* slab, const SlabGe
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
+__device__ __align__(16) const double g_zero16[2] = {0.0, 0.0};
+
 struct TileSet {
   int rb[4];     // first storage row of each 8-row tile
   int kind[4];   // 0 training rows, 1 the y row, 2 identity rows, 3 unused slot
@@ -150,63 +192,103 @@ struct TileSet {
 // acc[t][u] += A_t (8 x 32*kc, streamed from the slab) * B_u^T (shared memory) for the NTL tiles
 // of this warp.  NTL is a template parameter on purpose: predicated-off DMMAs still occupy the
 // FP64 pipe, so inactive tiles must not appear in the instruction stream at all.
+//
+// The A operand comes from L2 (~1000 cycles away, one 8-column step is only NTL x 128 cycles of
+// DMMA issue), so it has to run several steps ahead.  A register ring does not survive ptxas (it
+// loads into a temporary and copies into the ring slot right away, i.e. waits for every load in
+// the step that issued it), so the ring lives in shared memory and is filled with cp.async:
+// every lane copies its own 16-byte fragment into its own slot and cp.async.wait_group gives the
+// exact "all but the newest N" wait that scoreboards cannot express.  ring: this warp's
+// RING_BYTES of shared memory.
+constexpr int RING_BYTES = 8192;
 template <int NTL>
 __device__ __forceinline__ void k_chunk(double (&acc)[4][4][2], const TileSet& TS, const double* slab,
                                         const SlabGeom& G, const double* Bs, int bstride, int j0, int kc,
-                                        int r, int q) {
-  // L2 round trips cost ~1000 cycles here while one 8-column step is only NTL x 128 cycles of DMMA
-  // issue, so the A operand runs PF steps ahead in a register ring (statically indexed)
-  constexpr int PF = NTL == 1 ? 8 : (NTL == 2 ? 4 : 3);
+                                        int r, int q, unsigned ring) {
+  static_assert(NTL == 1 || NTL == 2, "ring sized for one or two tiles per warp");
+  constexpr int ST = NTL == 1 ? 16 : 8;   // ring stages: ST * NTL * 512 B == RING_BYTES, multiple of 4
   int jmin = j0 + kc;
 #pragma unroll
   for (int t = 0; t < NTL; ++t) jmin = min(jmin, TS.js[t]);
   const int jbeg = max(j0, jmin), jend = j0 + kc;
   if (jbeg >= jend) return;
   const int steps = 4 * (jend - jbeg);
-  double2 ring[PF][NTL];
+  const double* tb[NTL];
 #pragma unroll
-  for (int s = 0; s < PF; ++s) {
-    const int jj = jbeg + (s >> 2);
+  for (int t = 0; t < NTL; ++t) tb[t] = slab + (size_t)(TS.rb[t] + r) * 32 + 2 * q;
+  // B operand: rows 8u + r of the staged block row, 8 columns (64 bytes) per step
+  unsigned bsa[4];
 #pragma unroll
-    for (int t = 0; t < NTL; ++t) {
-      ring[s][t] = make_double2(0.0, 0.0);
-      if (s < steps && jj >= TS.js[t])
-        ring[s][t] = *reinterpret_cast<const double2*>(
-            slab + G.off(jj) + (size_t)(TS.rb[t] + r - 32 * jj) * 32 + 8 * (s & 3) + 2 * q);
+  for (int u = 0; u < 4; ++u)
+    bsa[u] = (unsigned)__cvta_generic_to_shared(Bs + (size_t)(8 * u + r) * bstride + 32 * (jbeg - j0) + 2 * q);
+  // copy the fragments of step sn into stage `stage`; always commits a (possibly empty) group so
+  // that the group count per step is uniform
+  auto issue = [&](int sn, int stage) {
+    if (sn < steps) {
+      const int jn = jbeg + (sn >> 2);
+      const int o = 32 * jn * (G.R - 16 * (jn + 1)) + 8 * (sn & 3);
+#pragma unroll
+      for (int t = 0; t < NTL; ++t) {
+        const double* src = jn >= TS.js[t] ? tb[t] + o : g_zero16;   // identity rows: zero before js
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(ring + (stage * NTL + t) * 512), "l"(src));
+      }
     }
-  }
-  for (int st0 = 0; st0 < steps; st0 += PF) {
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+#define BGP_LDS2(dst, addr) \
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"((dst).x), "=d"((dst).y) : "r"(addr))
 #pragma unroll
-    for (int s = 0; s < PF; ++s) {
+  for (int s = 0; s < ST - 1; ++s) issue(s, s);
+  // operands of the current / next step ping-pong between two statically indexed register sets
+  // (a copy "cur = next" would make ptxas wait for the loads in the step that issued them)
+  double2 av[2][NTL], bv[2][4];
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(ST - 2));
+#pragma unroll
+  for (int t = 0; t < NTL; ++t) BGP_LDS2(av[0][t], ring + t * 512);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) BGP_LDS2(bv[0][u], bsa[u]);
+  for (int st0 = 0; st0 < steps; st0 += ST) {
+#pragma unroll
+    for (int s = 0; s < ST; ++s) {
       const int st = st0 + s;
       if (st < steps) {
-        const int jcur = jbeg + (st >> 2);
-        double2 av[NTL];
+        // Everything in the step is volatile asm, so the order below is the issue order: the
+        // loads for step st+1 (its fragments have landed once at most ST-3 younger groups are
+        // pending) and the refill of the stage consumed in step st-1 sit between the DMMAs of
+        // step st, whose 16-cycle issue slots hide them.
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(ST - 3));
 #pragma unroll
-        for (int t = 0; t < NTL; ++t) av[t] = ring[s][t];
-        const int sn = st + PF, jn = jbeg + (sn >> 2);
-        if (sn < steps) {
-#pragma unroll
-          for (int t = 0; t < NTL; ++t)
-            ring[s][t] = (jn >= TS.js[t]) ? *reinterpret_cast<const double2*>(
-                                                slab + G.off(jn) + (size_t)(TS.rb[t] + r - 32 * jn) * 32 +
-                                                8 * (sn & 3) + 2 * q)
-                                          : make_double2(0.0, 0.0);
-        }
-        const int bcol = 32 * (jcur - j0) + 8 * (st & 3) + 2 * q;
-        double2 bv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          bv[u] = *reinterpret_cast<const double2*>(Bs + (size_t)(8 * u + r) * bstride + bcol);
-#pragma unroll
-        for (int t = 0; t < NTL; ++t) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) dmma(acc[t][u], av[t].x, bv[u].x);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) dmma(acc[t][u], av[t].y, bv[u].y);
+        for (int i = 0; i < 8 * NTL; ++i) {
+          const int h = i / (4 * NTL), t = (i >> 2) % NTL, u = i & 3;
+          constexpr int c = 0;
+          dmma(acc[t][u], h ? av[s & 1][t].y : av[s & 1][t].x, h ? bv[s & 1][u].y : bv[s & 1][u].x);
+          if (i < NTL) BGP_LDS2(av[(s & 1) ^ 1][i], ring + (((s + 1) % ST) * NTL + i) * 512);
+          if (i == NTL) issue(st + ST - 1, (s + ST - 1) % ST);
+          if (i > NTL && i <= NTL + 4) BGP_LDS2(bv[(s & 1) ^ 1][i - NTL - 1], bsa[i - NTL - 1] + 64 * (st + 1));
+          (void)c;
         }
       }
     }
+  }
+#undef BGP_LDS2
+  asm volatile("cp.async.wait_all;\n" ::);
+}
+
+// Gram values of a warp's tiles for panel k, requested before the K-loop so that their L2 round
+// trip is over when finish_tiles needs them (volatile asm: the loads stay where they are written)
+template <int NTL>
+__device__ __forceinline__ void prefetch_gram(double2 (&ginit)[2][4], const TileSet& TS, const double* slab,
+                                              const SlabGeom& G, int k, int npad, int r, int q) {
+  const int c0 = 32 * k;
+#pragma unroll
+  for (int t = 0; t < NTL; ++t) {
+    const int rowc = TS.kind[t] == 0 ? min(TS.rb[t] + r, npad - 1) : c0;
+    const double* src = slab + G.off(k) + (size_t)(rowc - c0) * 32 + 2 * q;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];\n"
+                   : "=d"(ginit[t][u].x), "=d"(ginit[t][u].y)
+                   : "l"(src + 8 * u));
   }
 }
 
@@ -215,19 +297,8 @@ template <int NTL>
 __device__ __forceinline__ void finish_tiles(double (&acc)[4][4][2], const TileSet& TS, const CholArgs& A,
                                              const double* Lt, const double* Wd, double* slab,
                                              const SlabGeom& G, int k, int n, int npad, int b, int r, int q,
-                                             double& zz) {
+                                             double& zz, const double2 (&ginit)[2][4]) {
   const int c0 = 32 * k;
-  // Gram values of my tiles for this panel: all loads issued together, branch-free
-  double2 ginit[NTL][4];
-  if (!A.dense) {
-#pragma unroll
-    for (int t = 0; t < NTL; ++t)
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int rowc = TS.kind[t] == 0 ? min(TS.rb[t] + r, npad - 1) : c0;
-        ginit[t][u] = *reinterpret_cast<const double2*>(slab + G.off(k) + (size_t)(rowc - c0) * 32 + 8 * u + 2 * q);
-      }
-  }
 #pragma unroll
   for (int t = 0; t < NTL; ++t) {
     const int row = TS.rb[t] + r;
@@ -347,7 +418,7 @@ __device__ __forceinline__ void cluster_barrier() {
 // update, potrf) redundantly -- it is deterministic, so no exchange is needed -- and split the
 // row tiles of the trailing update / panel solve; a cluster barrier per panel publishes the rows
 // each of them wrote to the (L2-resident) slab.
-constexpr int MAXT = 3;   // row tiles per warp and round
+constexpr int MAXT = 2;   // row tiles per warp and round
 
 template <int NW, int CS>
 __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
@@ -363,6 +434,11 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
   const int kch = P - 1 < KCH ? (P - 1 > 0 ? P - 1 : 1) : KCH;
   const int bstride = 32 * kch + 8;
   double* Bs = reinterpret_cast<double*>(smem_raw + ((sizeof(CholSmem<NW>) + 15) & ~size_t(15)));  // 32 x bstride
+  // after Bs: the K-split partial sums of the diagonal update (phase 1) and the warps' cp.async
+  // rings of the trailing update (phase 2) share one region
+  double* region = Bs + (size_t)32 * bstride;
+  double (*Part)[32 * PP] = reinterpret_cast<double (*)[32 * PP]>(region);
+  const unsigned ring = (unsigned)__cvta_generic_to_shared(region) + warp * RING_BYTES + lane * 16;
   if (A.prog) {
     const int* src = reinterpret_cast<const int*>(A.prog);
     int* dst = reinterpret_cast<int*>(&S.prog);
@@ -418,13 +494,13 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
         for (int t = 0; t < 4; ++t)
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            S.Part[warp][(8 * t + r) * PP + 8 * u + 2 * q] = acc[t][u][0];
-            S.Part[warp][(8 * t + r) * PP + 8 * u + 2 * q + 1] = acc[t][u][1];
+            Part[warp][(8 * t + r) * PP + 8 * u + 2 * q] = acc[t][u][0];
+            Part[warp][(8 * t + r) * PP + 8 * u + 2 * q + 1] = acc[t][u][1];
           }
       }
       __syncthreads();   // also makes the Gram panel (written earlier) visible to the whole CTA
       BGP_STAMP(1);
-      assemble_diag(A, slab, G, S.Part, S.Dblk, k, n, k > 0, tid, NW * 32);
+      assemble_diag(A, slab, G, Part, S.Dblk, k, n, k > 0, tid, NW * 32);
       __syncthreads();
       BGP_STAMP(2);
       // Warp 0 factors the diagonal block.  When K is not chunked the other warps do not wait for
@@ -436,7 +512,10 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
         if (f && lane == 0) S.fail = c0 + f;
         // L_kk -> slab (diag group rows of panel k)
         if (crank == 0)
-          for (int e = lane; e < 1024; e += 32) slab[G.off(k) + e] = S.Lt[(e >> 5) * LS + (e & 31)];
+#pragma unroll
+          for (int e = lane; e < 512; e += 32)
+            *reinterpret_cast<double2*>(slab + G.off(k) + 2 * e) =
+                *reinterpret_cast<const double2*>(S.Lt + (e >> 4) * LS + 2 * (e & 15));
         BGP_STAMP(3);
         if (overlap) asm volatile("bar.sync 2, %0;" ::"r"(NW * 32) : "memory");
       } else if (A.dbg && warp == (A.dbg_tid >> 5)) {
@@ -452,16 +531,16 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
       // tiles dealt evenly to the warps (up to four per warp and round)
       // 32-row groups below the diagonal and identity-row groups; with CS == 2 groups alternate
       // between the two CTAs of the cluster and the y tile belongs to rank 0
-      const int nmg = P - 1 - k, nag = A.aug ? k + 1 : 0;
-      const int my_mg = (nmg - crank + CS - 1) / CS;                 // groups crank, crank + CS, ...
-      const int a0 = ((crank - nmg) % CS + CS) % CS;                  // continue the deal over identity groups
-      const int my_ag = nag > a0 ? (nag - a0 + CS - 1) / CS : 0;
-      const int has_z = (CS == 1 || crank == 0) ? 1 : 0;
-      const int n_main_t = 4 * my_mg;
-      const int T = n_main_t + has_z + 4 * my_ag;
+      // tiles of this panel: the y tile, the 4 (P-1-k) tiles below the block, the identity-row
+      // tiles; the CTAs of a cluster take contiguous, equally long parts of that list
+      const int nmt = 4 * (P - 1 - k), nat = A.aug ? 4 * (k + 1) : 0;
+      const int Tg = 1 + nmt + nat;
+      // (rounded up, so that the y tile -- whose |z|^2 the epilogue of rank 0 sums -- stays on rank 0)
+      const int tlo = (Tg * crank + CS - 1) / CS, T = (Tg * (crank + 1) + CS - 1) / CS - tlo;
       // warp w owns the contiguous tiles [w0, w0 + mine); every warp runs the same number of
       // rounds (barriers inside when K is chunked), each with at most four of its tiles
-      const int nwk = overlap ? NW - 1 : NW;          // worker warps (warp 0 is busy when overlapping)
+      // worker warps (warp 0 is busy when overlapping)
+      const int nwk = overlap ? NW - 1 : NW;
       const int wrk = overlap ? warp - 1 : warp;
       const int tq = T / nwk, trm = T % nwk;
       const int mine = wrk < 0 ? 0 : tq + (wrk < trm ? 1 : 0);
@@ -477,19 +556,23 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
           const int ti = first + t;
           TS.rb[t] = c0; TS.kind[t] = 3; TS.js[t] = 0;   // kind 3: padding slot of the tile set
           if (t < ntl) {
-            if (ti < n_main_t) {
-              const int g = CS * (ti >> 2) + crank;
-              TS.rb[t] = 32 * (k + 1) + 32 * g + 8 * (ti & 3); TS.kind[t] = 0;
-            } else if (has_z && ti == n_main_t) {
+            const int gi = tlo + ti;
+            if (gi == 0) {
               TS.rb[t] = G.Rz; TS.kind[t] = 1;
+            } else if (gi <= nmt) {
+              TS.rb[t] = 32 * (k + 1) + 8 * (gi - 1); TS.kind[t] = 0;
             } else {
-              const int l2 = ti - n_main_t - has_z;
-              const int a = a0 + CS * (l2 >> 2);
-              TS.rb[t] = G.Ra + 32 * a + 8 * (l2 & 3); TS.kind[t] = 2; TS.js[t] = a;
+              const int l2 = gi - 1 - nmt;
+              TS.rb[t] = G.Ra + 8 * l2; TS.kind[t] = 2; TS.js[t] = l2 >> 2;
             }
           }
         }
         long long tph = clock64();
+        double2 ginit[2][4];
+        if (!A.dense) {
+          if (ntl == 2) prefetch_gram<2>(ginit, TS, slab, G, k, npad, r, q);
+          else if (ntl == 1) prefetch_gram<1>(ginit, TS, slab, G, k, npad, r, q);
+        }
 #pragma unroll
         for (int t = 0; t < 4; ++t)
 #pragma unroll
@@ -502,9 +585,8 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
             __syncthreads();
           }
           switch (ntl) {
-            case 3: k_chunk<3>(acc, TS, slab, G, Bs, bstride, j0, kc, r, q); break;
-            case 2: k_chunk<2>(acc, TS, slab, G, Bs, bstride, j0, kc, r, q); break;
-            case 1: k_chunk<1>(acc, TS, slab, G, Bs, bstride, j0, kc, r, q); break;
+            case 2: k_chunk<2>(acc, TS, slab, G, Bs, bstride, j0, kc, r, q, ring); break;
+            case 1: k_chunk<1>(acc, TS, slab, G, Bs, bstride, j0, kc, r, q, ring); break;
             default: break;
           }
         }
@@ -513,9 +595,8 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
         if (S.fail) continue;
         double zpart = 0.0;
         switch (ntl) {
-          case 3: finish_tiles<3>(acc, TS, A, S.Lt, &S.Wd[0][0], slab, G, k, n, npad, b, r, q, zpart); break;
-          case 2: finish_tiles<2>(acc, TS, A, S.Lt, &S.Wd[0][0], slab, G, k, n, npad, b, r, q, zpart); break;
-          case 1: finish_tiles<1>(acc, TS, A, S.Lt, &S.Wd[0][0], slab, G, k, n, npad, b, r, q, zpart); break;
+          case 2: finish_tiles<2>(acc, TS, A, S.Lt, &S.Wd[0][0], slab, G, k, n, npad, b, r, q, zpart, ginit); break;
+          case 1: finish_tiles<1>(acc, TS, A, S.Lt, &S.Wd[0][0], slab, G, k, n, npad, b, r, q, zpart, ginit); break;
           default: break;
         }
         zz += zpart;
@@ -560,7 +641,8 @@ static size_t chol_smem_bytes(int n) {
   const int kch = P - 1 < KCH ? (P - 1 > 0 ? P - 1 : 1) : KCH;
   size_t base = pick_nw(n) == 8 ? sizeof(CholSmem<8>) : sizeof(CholSmem<4>);
   base = (base + 15) & ~size_t(15);
-  return base + sizeof(double) * (size_t)32 * (32 * kch + 8);
+  const size_t part = sizeof(double) * 4 * 32 * PP, rings = (size_t)pick_nw(n) * RING_BYTES;
+  return base + sizeof(double) * (size_t)32 * (32 * kch + 8) + (part > rings ? part : rings);
 }
 
 // largest portable cluster size that still fits the batch on the chip
