@@ -17,7 +17,6 @@ namespace bgp {
 constexpr int KCH = 15;        // previous panels staged in shared memory at once
 constexpr int LS = 40;         // row stride of the factored diagonal block read by DMMA (== 8 mod 16)
 constexpr int PS = 33;         // row stride of the diagonal block being factored (odd: conflict-free)
-constexpr int PP = 34;         // row stride of the K-split partial blocks
 
 template <int NW>
 struct CholSmem {
@@ -371,41 +370,57 @@ __device__ __forceinline__ void finish_tiles(double (&acc)[4][4][2], const TileS
   }
 }
 
-// Dblk = init(diagonal block kk) - sum of the four partial products (when kk > 0)
-__device__ __forceinline__ void assemble_diag(const CholArgs& A, const double* slab, const SlabGeom& G,
-                                              const double (*Part)[32 * PP], double* Dblk, int kk, int n,
-                                              bool with_part, int t0, int nthreads) {
+// The Gram values of the diagonal block a thread assembles (elements tid, tid + nthreads, ...),
+// requested at the top of the panel so that their L2 round trip overlaps the stage + diagonal GEMM
+template <int NE>
+__device__ __forceinline__ void prefetch_diag(double (&g)[NE], const CholArgs& A, const double* slab,
+                                              const SlabGeom& G, int kk, int n, int t0, int nthreads) {
   const int c0 = 32 * kk;
-  // all loads of a thread are issued before the first use (clamped, branch-free addresses)
-  for (int e0 = t0; e0 < 1024; e0 += 8 * nthreads) {
-    double g[8];
 #pragma unroll
-    for (int s = 0; s < 8; ++s) {
-      const int e = e0 + s * nthreads;
-      const int rl = (e >> 5) & 31, cl = e & 31;
-      const int row = min(c0 + rl, n - 1), col = min(c0 + cl, n - 1);
-      g[s] = (e < 1024) ? (A.dense ? A.dense[(size_t)row * A.ldd + col]
-                                   : __ldcg(slab + G.off(kk) + (size_t)(row - c0) * 32 + (col - c0)))
-                        : 0.0;
+  for (int s = 0; s < NE; ++s) {
+    const int e = t0 + s * nthreads;
+    const int rl = (e >> 5) & 31, cl = e & 31;
+    const int row = min(c0 + rl, n - 1), col = min(c0 + cl, n - 1);
+    if (A.dense) {
+      g[s] = A.dense[(size_t)row * A.ldd + col];
+    } else {
+      asm volatile("ld.global.cg.f64 %0, [%1];\n"
+                   : "=d"(g[s])
+                   : "l"(slab + G.off(kk) + (size_t)(row - c0) * 32 + (col - c0)));
     }
+  }
+}
+
+// Dblk = init(diagonal block kk) - sum of the NP K-split partial products (when kk > 0); a partial
+// holds the ten lower 8x8 sub-tiles in fragment order: [sub-tile][lane][2]
+constexpr int PART_DOUBLES = 10 * 64;
+template <int NE, int NP>
+__device__ __forceinline__ void assemble_diag(const double (&g)[NE], const CholArgs& A, const double* Part,
+                                              double* Dblk, int kk, int n, bool with_part, int t0, int nthreads) {
+  const int c0 = 32 * kk;
 #pragma unroll
-    for (int s = 0; s < 8; ++s) {
-      const int e = e0 + s * nthreads;
-      if (e >= 1024) continue;
-      const int rl = e >> 5, cl = e & 31;
-      double v = 0.0;
-      if (cl <= rl) {
-        const int row = c0 + rl, col = c0 + cl;
-        if (row < n && col < n) {
-          v = g[s] + ((A.dense && row == col) ? A.jitter : 0.0);
-          if (with_part) v -= (Part[0][rl * PP + cl] + Part[1][rl * PP + cl]) +
-                              (Part[2][rl * PP + cl] + Part[3][rl * PP + cl]);
-        } else {
-          v = (row == col) ? 1.0 : 0.0;
+  for (int s = 0; s < NE; ++s) {
+    const int e = t0 + s * nthreads;
+    if (e >= 1024) continue;
+    const int rl = e >> 5, cl = e & 31;
+    double v = 0.0;
+    if (cl <= rl) {
+      const int row = c0 + rl, col = c0 + cl;
+      if (row < n && col < n) {
+        v = g[s] + ((A.dense && row == col) ? A.jitter : 0.0);
+        if (with_part) {
+          const int t = rl >> 3, u = cl >> 3;
+          const int idx = (t * (t + 1) / 2 + u) * 64 + (4 * (rl & 7) + ((cl & 7) >> 1)) * 2 + (cl & 1);
+          double sum = 0.0;
+#pragma unroll
+          for (int w = 0; w < NP; ++w) sum += Part[w * PART_DOUBLES + idx];
+          v -= sum;
         }
+      } else {
+        v = (row == col) ? 1.0 : 0.0;
       }
-      Dblk[rl * PS + cl] = v;
     }
+    Dblk[rl * PS + cl] = v;
   }
 }
 
@@ -437,7 +452,7 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
   // after Bs: the K-split partial sums of the diagonal update (phase 1) and the warps' cp.async
   // rings of the trailing update (phase 2) share one region
   double* region = Bs + (size_t)32 * bstride;
-  double (*Part)[32 * PP] = reinterpret_cast<double (*)[32 * PP]>(region);
+  double* Part = region;   // NW partials of PART_DOUBLES
   const unsigned ring = (unsigned)__cvta_generic_to_shared(region) + warp * RING_BYTES + lane * 16;
   if (A.prog) {
     const int* src = reinterpret_cast<const int*>(A.prog);
@@ -462,45 +477,43 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
       const int c0 = 32 * k;
       BGP_STAMP(0);
       // ------------------------------------------------ phase 1: diagonal block
-      double acc[4][4][2];
+      constexpr int NE = 1024 / (NW * 32);
+      double gd[NE];
+      prefetch_diag<NE>(gd, A, slab, G, k, n, tid, NW * 32);
+      // D -= sum_j L[k,j] L[k,j]^T: every warp takes every NW-th 8-column step of the staged block
+      // row and accumulates the ten lower 8x8 sub-tiles (the fragments of the four row tiles are
+      // both the A and the B operands)
+      double dacc[10][2];
 #pragma unroll
-      for (int t = 0; t < 4; ++t)
-#pragma unroll
-        for (int u = 0; u < 4; ++u) acc[t][u][0] = acc[t][u][1] = 0.0;
+      for (int i = 0; i < 10; ++i) dacc[i][0] = dacc[i][1] = 0.0;
       const int nchunks = (k + kch - 1) / kch;
       for (int ch = 0; ch < nchunks; ++ch) {
         const int j0 = ch * kch, kc = min(kch, k - j0);
         __syncthreads();
         stage_block_row(slab, G, Bs, bstride, c0, j0, kc, tid, NW * 32);
         __syncthreads();
-        if (warp < 4) {
-          for (int c8 = warp; c8 < 4 * kc; c8 += 4) {
-            double2 f[4];
+        for (int c8 = warp; c8 < 4 * kc; c8 += NW) {
+          double2 f[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            f[t] = *reinterpret_cast<const double2*>(Bs + (size_t)(8 * t + r) * bstride + 8 * c8 + 2 * q);
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
 #pragma unroll
             for (int t = 0; t < 4; ++t)
-              f[t] = *reinterpret_cast<const double2*>(Bs + (size_t)(8 * t + r) * bstride + 8 * c8 + 2 * q);
 #pragma unroll
-            for (int t = 0; t < 4; ++t)
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                dmma(acc[t][u], f[t].x, f[u].x);
-                dmma(acc[t][u], f[t].y, f[u].y);
-              }
-          }
+              for (int u = 0; u <= t; ++u)
+                dmma(dacc[t * (t + 1) / 2 + u], h ? f[t].y : f[t].x, h ? f[u].y : f[u].x);
         }
       }
-      if (warp < 4) {
+      if (k > 0) {
 #pragma unroll
-        for (int t = 0; t < 4; ++t)
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            Part[warp][(8 * t + r) * PP + 8 * u + 2 * q] = acc[t][u][0];
-            Part[warp][(8 * t + r) * PP + 8 * u + 2 * q + 1] = acc[t][u][1];
-          }
+        for (int i = 0; i < 10; ++i)
+          *reinterpret_cast<double2*>(Part + warp * PART_DOUBLES + i * 64 + lane * 2) = make_double2(dacc[i][0], dacc[i][1]);
       }
       __syncthreads();   // also makes the Gram panel (written earlier) visible to the whole CTA
       BGP_STAMP(1);
-      assemble_diag(A, slab, G, Part, S.Dblk, k, n, k > 0, tid, NW * 32);
+      assemble_diag<NE, NW>(gd, A, Part, S.Dblk, k, n, k > 0, tid, NW * 32);
       __syncthreads();
       BGP_STAMP(2);
       // Warp 0 factors the diagonal block.  When K is not chunked the other warps do not wait for
@@ -568,6 +581,7 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
           }
         }
         long long tph = clock64();
+        double acc[4][4][2];
         double2 ginit[2][4];
         if (!A.dense) {
           if (ntl == 2) prefetch_gram<2>(ginit, TS, slab, G, k, npad, r, q);
@@ -641,7 +655,7 @@ static size_t chol_smem_bytes(int n) {
   const int kch = P - 1 < KCH ? (P - 1 > 0 ? P - 1 : 1) : KCH;
   size_t base = pick_nw(n) == 8 ? sizeof(CholSmem<8>) : sizeof(CholSmem<4>);
   base = (base + 15) & ~size_t(15);
-  const size_t part = sizeof(double) * 4 * 32 * PP, rings = (size_t)pick_nw(n) * RING_BYTES;
+  const size_t part = sizeof(double) * pick_nw(n) * PART_DOUBLES, rings = (size_t)pick_nw(n) * RING_BYTES;
   return base + sizeof(double) * (size_t)32 * (32 * kch + 8) + (part > rings ? part : rings);
 }
 
