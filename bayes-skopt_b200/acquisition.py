@@ -220,7 +220,17 @@ def evaluate_acquisitions(X, gpr, acquisition_functions=None, n_samples=10, prog
     Xd = e.to_dev(X)
     y_mean = float(np.atleast_1d(gpr.y_train_mean_)[0])
     y_std = float(np.atleast_1d(gpr.y_train_std_)[0])
-    mu = sd = None
+    mu = sd = pd_info = None
+
+    def _check_pd():
+        nonlocal pd_info
+        if pd_info is not None:
+            info, pd_info = e.to_host(pd_info), None
+            if np.any(info != 0):
+                raise np.linalg.LinAlgError(
+                    "The kernel, %s, is not returning a positive definite matrix. Try gradually increasing "
+                    "the 'alpha' parameter of your GaussianProcessRegressor estimator." % gpr.kernel_)
+
     all_builtin = all(type(a).__call__ is _DeviceUncertainty.__call__ for a in acquisition_functions
                       if isinstance(a, UncertaintyAcquisition))
     if sharded and not all_builtin:
@@ -229,11 +239,9 @@ def evaluate_acquisitions(X, gpr, acquisition_functions=None, n_samples=10, prog
     if has_unc and not sharded:
         th = e.to_dev(gpr.chain_[trace_sample_i])
         f = e.factorize(th)
-        info = e.to_host(f.info)
-        if np.any(info != 0):
-            raise np.linalg.LinAlgError(
-                "The kernel, %s, is not returning a positive definite matrix. Try gradually increasing "
-                "the 'alpha' parameter of your GaussianProcessRegressor estimator." % gpr.kernel_)
+        # the positive-definiteness flags are read back after the sweep has been enqueued (see
+        # _check_pd below): a host round trip here would leave the GPU idle
+        pd_info = f.info
         mu, sd, _, _ = e.predict(f, Xd, noise_off=True, y_mean=y_mean, y_std=y_std)
     # host-RNG consumption in the reference's order: per theta, MES draws (global numpy RNG) in
     # acquisition order; the first SampleAcquisition triggers one sample_y (random_state)
@@ -272,10 +280,13 @@ def evaluate_acquisitions(X, gpr, acquisition_functions=None, n_samples=10, prog
         if isinstance(acq, _DeviceUncertainty) and type(acq).__call__ is _DeviceUncertainty.__call__:
             g = np.stack(gumbels[j]) if j in gumbels else None
             out, _per, _skipped, _ = acq.device_eval(e, mu, sd, kwargs, gumbel=g)
-            acq_output[j] += e.to_host(out)
+            res = e.to_host(out)
+            _check_pd()
+            acq_output[j] += res
         elif isinstance(acq, UncertaintyAcquisition):
             if mu_h is None:
                 mu_h, sd_h = e.to_host(mu), e.to_host(sd)
+                _check_pd()
             for s in range(S):
                 tmp = acq(mu_h[s], sd_h[s], **kwargs)
                 if np.all(np.isfinite(tmp)):
@@ -285,4 +296,5 @@ def evaluate_acquisitions(X, gpr, acquisition_functions=None, n_samples=10, prog
                 tmp = acq(samples[s], **kwargs)
                 if np.all(np.isfinite(tmp)):
                     acq_output[j] += tmp / n_samples
+    _check_pd()
     return acq_output

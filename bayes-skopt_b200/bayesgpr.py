@@ -103,17 +103,49 @@ class BayesGPR:
         with np.errstate(divide="ignore"):
             return np.array(self.kernel_.theta, dtype=np.float64)
 
-    def _refactor(self):
+    def _refactor(self, lazy=False):
+        """Factorises at the current theta.  ``lazy`` only enqueues the work: the positive-
+        definiteness check (and its LinAlgError) then happens at the first use of the factor."""
         e = self._eng()
-        f = e.factorize(self._theta_for_device()[None, :])
-        info = int(e.to_host(f.info)[0])
-        if info != 0:
-            raise np.linalg.LinAlgError(
-                "The kernel, %s, is not returning a positive definite matrix. Try gradually "
-                "increasing the 'alpha' parameter of your GaussianProcessRegressor estimator."
-                % self.kernel_, f"{info}-th leading minor of the array is not positive definite")
-        self._factor = f
+        self._factor_pending = e.factorize(self._theta_for_device()[None, :])
+        self._factor_value = None
         self._dense = {}
+        self._lml_value = None
+        if not lazy:
+            self._factor  # noqa: B018  (materialises: synchronises and checks)
+
+    @property
+    def _factor(self):
+        f = getattr(self, "_factor_pending", None)
+        if f is not None:
+            self._factor_pending = None
+            info = int(self._eng().to_host(f.info)[0])
+            if info != 0:
+                raise np.linalg.LinAlgError(
+                    "The kernel, %s, is not returning a positive definite matrix. Try gradually "
+                    "increasing the 'alpha' parameter of your GaussianProcessRegressor estimator."
+                    % self.kernel_, f"{info}-th leading minor of the array is not positive definite")
+            self._factor_value = f
+        return getattr(self, "_factor_value", None)
+
+    @_factor.setter
+    def _factor(self, f):
+        self._factor_pending = None
+        self._factor_value = f
+
+    @property
+    def log_marginal_likelihood_value_(self):
+        """LML at the current theta (sklearn attribute); read back from the device on first use."""
+        if getattr(self, "_lml_value", None) is None and getattr(self, "_lml_from_factor", False):
+            f = self._factor
+            if f is not None:
+                self._lml_value = float(self._eng().to_host(f.lml)[0])
+        return getattr(self, "_lml_value", None)
+
+    @log_marginal_likelihood_value_.setter
+    def log_marginal_likelihood_value_(self, v):
+        self._lml_from_factor = False
+        self._lml_value = v
 
     def _dense_attr(self, name, what):
         if name in self._dense:
@@ -333,8 +365,11 @@ class BayesGPR:
             self.chain_ = np.concatenate([self.chain_, chain])
         else:
             self.chain_ = chain
-        self.theta = geometric_median(self.chain_)
-        self.log_marginal_likelihood_value_ = float(e.to_host(self._factor.lml)[0])
+        # point estimate: the factorisation at the geometric median is only enqueued here; its
+        # LinAlgError check and the LML read-back happen at the first use (no host round trip)
+        self.kernel_.theta = geometric_median(self.chain_)
+        self._refactor(lazy=True)
+        self._lml_from_factor = True
         self.pos_ = pos_out
 
     def _host_stepped_mcmc(self, pos, n_steps, seed, a, host_fn):

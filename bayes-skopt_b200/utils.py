@@ -15,24 +15,27 @@ def geometric_median(X, eps=1e-5):
     (bask/utils.py:21-65).  O(N p) per iteration on a (N, p) chain: stays on the host."""
     X = np.asarray(X, dtype=np.float64)
     y = np.mean(X, 0)
+    N = len(X)
     while True:
-        D = np.sqrt(((X - y) ** 2).sum(axis=1))[:, None]
-        nonzeros = (D != 0)[:, 0]
-        Dinv = 1 / D[nonzeros]
-        Dinvs = np.sum(Dinv)
-        W = Dinv / Dinvs
-        T = np.sum(W * X[nonzeros], 0)
-        num_zeros = len(X) - np.sum(nonzeros)
-        if num_zeros == 0:
-            y1 = T
-        elif num_zeros == len(X):
-            return y
+        diff = X - y
+        D = np.sqrt(np.einsum("ij,ij->i", diff, diff))
+        nz = D != 0
+        if nz.all():
+            Dinv = 1.0 / D
+            y1 = (Dinv / Dinv.sum()) @ X
         else:
+            num_zeros = N - int(nz.sum())
+            if num_zeros == N:
+                return y
+            Dinv = 1.0 / D[nz]
+            Dinvs = Dinv.sum()
+            T = (Dinv / Dinvs) @ X[nz]
             R = (T - y) * Dinvs
             r = np.linalg.norm(R)
             rinv = 0 if r == 0 else num_zeros / r
             y1 = max(0, 1 - rinv) * T + min(1, rinv) * y
-        if np.sqrt(((y - y1) ** 2).sum()) < eps:
+        d = y - y1
+        if np.sqrt(d @ d) < eps:
             return y1
         y = y1
 
