@@ -26,6 +26,17 @@ import time
 
 import numpy as np
 
+# Libraries (NCCL's version banner, torchrun notices) may write to stdout; the contract is ONE JSON
+# line there, so file descriptor 1 is pointed at stderr for the whole run and the line is written to
+# the saved descriptor at the end.
+_STDOUT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_STDOUT_FD, (json.dumps(line) + "\n").encode())
+
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
@@ -165,7 +176,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                              "sample": sample, "detail": detail},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------ GPU arm
@@ -353,7 +364,7 @@ def run_b200(args):
                 "sample": "48 log-posterior evals + 1 theta-setter + predict/MES over 400 candidates at n=500, "
                           "extrapolated linearly to the full cycle (1536 evals + 10 x 10000 candidates)",
                 "cycle_s_extrapolated": cyc, "detail": detail}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
