@@ -13,7 +13,10 @@
 
 namespace bgp {
 
-// Xt[b][leaf][dim][npad] = X[i][dim] / length_scale(theta_b, leaf, dim), zero padded
+// Xt[b][leaf][dim][nx] = X[i][dim] / length_scale(theta_b, leaf, dim), zero padded to nx = 32 P + 64
+// rows so that the 64-row chunks of gram_kernel can read their eight rows without clamping
+__host__ __device__ inline int gram_nx(int n) { return 32 * ((n + 31) / 32) + 64; }
+
 __global__ void __launch_bounds__(256) scale_x_kernel(GramArgs A) {
   __shared__ DevProgram PR;
   __shared__ ThetaParams TP;
@@ -26,7 +29,7 @@ __global__ void __launch_bounds__(256) scale_x_kernel(GramArgs A) {
   __syncthreads();
   resolve_theta(PR, A.theta + (size_t)b * PR.n_theta, A.fixed_ls, TP, tid, 256);
   __syncthreads();
-  const int npad = 32 * ((A.n + 31) / 32), d = A.d;
+  const int npad = gram_nx(A.n), d = A.d;
   double* Xt = A.xt + (size_t)b * A.xt_stride;
   for (int e = blockIdx.x * 256 + tid; e < PR.n_leaves * d * npad; e += gridDim.x * 256) {
     const int l = e / (d * npad), rem = e - l * d * npad, kk = rem / npad, i = rem - kk * npad;
@@ -56,7 +59,7 @@ __global__ void __launch_bounds__(256) gram_kernel(GramArgs A) {
   resolve_theta(PR, A.theta + (size_t)b * PR.n_theta, A.fixed_ls, TP, tid, 256);
   __syncthreads();
   const SlabGeom G = SlabGeom::make(n, A.aug != 0);
-  const int npad = 32 * G.P;
+  const int npad = gram_nx(n);
   const double* Xt = A.xt + (size_t)b * A.xt_stride;
   double* base = A.slabs + (size_t)b * G.doubles() + G.off(k);
   constexpr int RB = 8;
@@ -67,13 +70,20 @@ __global__ void __launch_bounds__(256) gram_kernel(GramArgs A) {
       double r2[RB];
 #pragma unroll
       for (int a = 0; a < RB; ++a) r2[a] = 0.0;
-      for (int kk = 0; kk < d; ++kk) {
-        const double* xr = Xt + (size_t)kk * npad;
-        const double xc = xr[col];
+      // the eight rows of a warp are contiguous in Xt: four 16-byte loads per dimension, no
+      // per-element address arithmetic (r0 is a multiple of 8, the row stride a multiple of 32)
+      const double* xr = Xt + r0;
+      const double* xcp = Xt + col;
+      for (int kk = 0; kk < d; ++kk, xr += npad, xcp += npad) {
+        const double xc = *xcp;
+        double2 rv[RB / 2];
 #pragma unroll
-        for (int a = 0; a < RB; ++a) {
-          const double t = xr[min(r0 + a, npad - 1)] - xc;
-          r2[a] = fma(t, t, r2[a]);
+        for (int a = 0; a < RB / 2; ++a) rv[a] = reinterpret_cast<const double2*>(xr)[a];
+#pragma unroll
+        for (int a = 0; a < RB / 2; ++a) {
+          const double t0 = rv[a].x - xc, t1 = rv[a].y - xc;
+          r2[2 * a] = fma(t0, t0, r2[2 * a]);
+          r2[2 * a + 1] = fma(t1, t1, r2[2 * a + 1]);
         }
       }
       const double cval = TP.opval[PR.fast_const], wval = TP.opval[PR.fast_white];
@@ -116,7 +126,7 @@ __global__ void __launch_bounds__(256) gram_kernel(GramArgs A) {
 }
 
 size_t gram_xt_doubles(int n, int d, int n_leaves) {
-  return (size_t)(n_leaves > 0 ? n_leaves : 1) * d * (32 * ((n + 31) / 32));
+  return (size_t)(n_leaves > 0 ? n_leaves : 1) * d * gram_nx(n);
 }
 
 cudaError_t launch_gram(const GramArgs& A, cudaStream_t stream) {
