@@ -552,9 +552,14 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
       const int tlo = (Tg * crank + CS - 1) / CS, T = (Tg * (crank + 1) + CS - 1) / CS - tlo;
       // warp w owns the contiguous tiles [w0, w0 + mine); every warp runs the same number of
       // rounds (barriers inside when K is chunked), each with at most four of its tiles
-      // worker warps (warp 0 is busy when overlapping)
+      // worker warps (warp 0 is busy when overlapping).  The deal starts with the warps that have
+      // an SM sub-partition to themselves and ends with warp NW/2, which shares its FP64 pipe with
+      // the potrf warp: with few tiles left the K-loops run alone on their pipes and the
+      // dependent DFMA chain of the potrf does not queue behind DMMAs.
       const int nwk = overlap ? NW - 1 : NW;
-      const int wrk = overlap ? warp - 1 : warp;
+      const int wrk = !overlap ? warp
+                      : NW == 8 ? (warp == 0 ? -1 : warp == 4 ? 6 : warp < 4 ? warp - 1 : warp - 2)
+                                : warp - 1;
       const int tq = T / nwk, trm = T % nwk;
       const int mine = wrk < 0 ? 0 : tq + (wrk < trm ? 1 : 0);
       const int w0 = wrk < 0 ? 0 : wrk * tq + min(wrk, trm);

@@ -37,13 +37,14 @@ __global__ void __launch_bounds__(256) scale_x_kernel(GramArgs A) {
   }
 }
 
-// CTA (64-row chunk of panel k, theta b): 64 x 32 entries of the lower triangle.  A warp takes
-// eight rows (eight independent sqrt/exp chains), lanes are the 32 columns.  Chunks of all panels
+// CTA (32-row chunk of panel k, theta b): 32 x 32 entries of the lower triangle.  A warp takes
+// four rows (four independent sqrt/exp chains; 32 registers, full occupancy), lanes are the 32 columns.  Chunks of all panels
 // are enumerated along blockIdx.x so that every CTA has the same amount of work.
-constexpr int GRAM_ROWS = 64;
+constexpr int GRAM_RB = 4;                 // rows per warp
+constexpr int GRAM_ROWS = 8 * GRAM_RB;     // rows per CTA
 __host__ __device__ inline int gram_chunks(int n, int k) { return (n - 32 * k + GRAM_ROWS - 1) / GRAM_ROWS; }
 
-__global__ void __launch_bounds__(256) gram_kernel(GramArgs A) {
+__global__ void __launch_bounds__(256, 6) gram_kernel(GramArgs A) {
   __shared__ DevProgram PR;
   __shared__ ThetaParams TP;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -62,7 +63,7 @@ __global__ void __launch_bounds__(256) gram_kernel(GramArgs A) {
   const int npad = gram_nx(n);
   const double* Xt = A.xt + (size_t)b * A.xt_stride;
   double* base = A.slabs + (size_t)b * G.doubles() + G.off(k);
-  constexpr int RB = 8;
+  constexpr int RB = GRAM_RB;
   const int c0 = 32 * k, col = c0 + lane;
   {
     const int r0 = c0 + GRAM_ROWS * chunk + RB * warp;
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(256) gram_kernel(GramArgs A) {
 #pragma unroll
       for (int a = 0; a < RB; ++a) r2[a] = 0.0;
       // the eight rows of a warp are contiguous in Xt: four 16-byte loads per dimension, no
-      // per-element address arithmetic (r0 is a multiple of 8, the row stride a multiple of 32)
+      // per-element address arithmetic (r0 is a multiple of 4, the row stride a multiple of 32)
       const double* xr = Xt + r0;
       const double* xcp = Xt + col;
       for (int kk = 0; kk < d; ++kk, xr += npad, xcp += npad) {
