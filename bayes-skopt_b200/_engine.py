@@ -169,6 +169,10 @@ class Engine:
         with torch.cuda.stream(self.stream):
             return torch.empty(*shape, dtype=dtype, device=self.device)
 
+    def zeros(self, *shape, dtype=_F64):
+        with torch.cuda.stream(self.stream):
+            return torch.zeros(*shape, dtype=dtype, device=self.device)
+
     def to_host(self, t):
         self.stream.synchronize()
         return t.cpu().numpy()
@@ -177,12 +181,18 @@ class Engine:
         self.stream.synchronize()
 
     # ------------------------------------------------------------------ model set-up
-    def set_kernel(self, kernel):
+    def set_kernel(self, kernel, n_warp=0):
+        """Uploads the kernel program.  ``n_warp`` = d switches input warping on: theta rows then
+        are ``[kernel theta, log a_1..a_d, log b_1..b_d]`` (bask/bayesgpr.py:351-365) and
+        ``self.p`` is the full row length, ``self.p_kernel`` the kernel's own part."""
         ops, fixed_ls, p = compile_kernel(kernel)
         arr = (Op * len(ops))(*ops)
         fl = (C.c_double * max(1, len(fixed_ls)))(*fixed_ls)
         check(self.lib.bgp_set_kernel(self.h, arr, len(ops), p, fl, len(fixed_ls)), "bgp_set_kernel")
-        self.p = p
+        if n_warp:
+            check(self.lib.bgp_set_warp(self.h, int(n_warp)), "bgp_set_warp")
+        self.p_kernel, self.n_warp = p, int(n_warp)
+        self.p = p + 2 * int(n_warp)
 
     def set_priors(self, table):
         if table is None:
@@ -287,10 +297,9 @@ class Engine:
         if buffers is None or buffers["chain"].shape != (n_steps, W, p):
             buffers = dict(pos=self.empty(W, p), lp=self.empty(W), chain=self.empty(n_steps, W, p),
                            lpc=self.empty(n_steps, W), acc=self.empty(W, dtype=torch.int32))
+        src = pos if torch.is_tensor(pos) else self.to_dev(pos)     # pinned staging ring, engine stream
         with torch.cuda.stream(self.stream):
-            buffers["pos"].copy_(pos if torch.is_tensor(pos) else
-                                 torch.as_tensor(np.ascontiguousarray(pos, dtype=np.float64)).pin_memory(),
-                                 non_blocking=True)
+            buffers["pos"].copy_(src, non_blocking=True)
         check(self.lib.bgp_mcmc_run(self.h, _ptr(buffers["pos"]), _ptr(buffers["lp"]), W, n_steps, float(a),
                                     C.c_uint64(int(seed) & (2 ** 64 - 1)), _ptr(buffers["chain"]),
                                     _ptr(buffers["lpc"]), _ptr(buffers["acc"]), self._st), "bgp_mcmc_run")

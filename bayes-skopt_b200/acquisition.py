@@ -141,7 +141,8 @@ def _variance_reduction_dev(gp, Xd, points_idx):
     f = gp._factor
     m = Xd.shape[0]
     _mu, sd, _, v = e.predict(f, Xd, thetas_dev=th, noise_off=False, y_mean=0.0, y_std=1.0, want_v=True)
-    s_i = sd[0] * sd[0]
+    with torch.cuda.stream(e.stream):   # torch ops must be ordered with the library's kernels
+        s_i = sd[0] * sd[0]
     if points_idx is None:
         cov = e.empty(m, m)
         _lib.check(e.lib.bgp_posterior_cov(e.h, th.data_ptr(), v[0].data_ptr(), Xd.data_ptr(), m, v.shape[2], 1,
@@ -151,13 +152,14 @@ def _variance_reduction_dev(gp, Xd, points_idx):
                                         out.data_ptr(), e._st), "bgp_vr_combine")
         e.launches += 2
         return out
-    idx = torch.as_tensor(np.asarray(points_idx, dtype=np.int64), device=e.device)
+    idx = e.to_dev(np.asarray(points_idx, dtype=np.int64), dtype=torch.int64)   # on the engine's stream
     with torch.cuda.stream(e.stream):
         vt = v[0].index_select(0, idx)[:, : e.n].contiguous()         # (R, n) whitened Thompson points
         Xt = Xd.index_select(0, idx).contiguous()
+        assert vt[None].is_contiguous()
     R = vt.shape[0]
     _mu2, _sd2, dots, _ = e.predict(f, Xd, thetas_dev=th, noise_off=False, y_mean=0.0, y_std=1.0,
-                                    zextra=vt[None].contiguous())
+                                    zextra=vt[None])
     out = e.empty(m)
     _lib.check(e.lib.bgp_pvrs_combine(e.h, th.data_ptr(), Xt.data_ptr(), R, Xd.data_ptr(), m, dots.data_ptr(),
                                       vt.data_ptr(), s_i.data_ptr(), out.data_ptr(), e._st), "bgp_pvrs_combine")

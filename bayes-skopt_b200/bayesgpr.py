@@ -29,7 +29,7 @@ from sklearn.utils import check_random_state
 from . import _lib
 from ._engine import Engine, find_zeroable_white
 from .priors import as_device_priors
-from .utils import geometric_median, guess_priors
+from .utils import geometric_median, guess_priors, validate_zeroone
 
 __all__ = ["BayesGPR"]
 
@@ -58,10 +58,6 @@ class BayesGPR:
     def __init__(self, kernel=None, alpha=1e-10, optimizer="fmin_l_bfgs_b", n_restarts_optimizer=0,
                  normalize_y=False, warp_inputs=False, copy_X_train=True, random_state=None,
                  noise="gaussian", device=None):
-        if warp_inputs:
-            raise NotImplementedError(
-                "warp_inputs=True (Beta-CDF input warping, bask/bayesgpr.py:219-316) is not "
-                "implemented on the B200 path yet")
         self._kernel = None if kernel is None else kernel.clone_with_theta(kernel.theta)
         self.kernel = kernel
         self.alpha = alpha
@@ -69,7 +65,7 @@ class BayesGPR:
         self.optimizer = optimizer
         self.n_restarts_optimizer = n_restarts_optimizer
         self.normalize_y = normalize_y
-        self.warp_inputs = False
+        self.warp_inputs = bool(warp_inputs)
         self.copy_X_train = copy_X_train
         self.random_state = check_random_state(random_state)
         self.noise = noise
@@ -94,14 +90,24 @@ class BayesGPR:
     def _upload_model(self, structure_changed):
         e = self._eng()
         if structure_changed:
-            e.set_kernel(self.kernel_)
+            e.set_kernel(self.kernel_, n_warp=self._X_train.shape[1] if self.warp_inputs else 0)
             self._prior_key = None
         alpha = self.alpha
         e.set_data(self._X_train, self.y_train_, alpha)
 
-    def _theta_for_device(self):
+    def _theta_for_device(self, theta=None):
+        """Device theta row for kernel hyper-parameters ``theta`` (default: the point estimate):
+        with input warping the current warp parameters are appended (log a, then log b; zeros,
+        i.e. the identity warp, before the first ``create_warpers``)."""
         with np.errstate(divide="ignore"):
-            return np.array(self.kernel_.theta, dtype=np.float64)
+            th = np.array(self.kernel_.theta if theta is None else theta, dtype=np.float64)
+        if self.warp_inputs:
+            d = self._X_train.shape[1]
+            a = getattr(self, "warp_alphas_", np.zeros(d))
+            b = getattr(self, "warp_betas_", np.zeros(d))
+            th = np.concatenate([th, a, b], axis=-1) if th.ndim == 1 else \
+                np.concatenate([th, np.tile(a, (len(th), 1)), np.tile(b, (len(th), 1))], axis=1)
+        return th
 
     def _refactor(self, lazy=False):
         """Factorises at the current theta.  ``lazy`` only enqueues the work: the positive-
@@ -180,20 +186,57 @@ class BayesGPR:
 
     @property
     def X_train_(self):
-        return getattr(self, "_X_train", None)
+        """Training inputs; the warped instances when ``warp_inputs=True`` and warpers exist
+        (bask/bayesgpr.py:219-247).  The device always holds the original inputs and warps them
+        per theta itself."""
+        X = getattr(self, "_X_train", None)
+        if X is not None and self.warp_inputs and hasattr(self, "warpers_"):
+            if getattr(self, "_X_train_warped", None) is None:
+                self._X_train_warped = self.warp(X)
+            return self._X_train_warped
+        return X
 
     @X_train_.setter
     def X_train_(self, X_train):
         self._X_train = np.copy(X_train) if self.copy_X_train else X_train
+        self._X_train_warped = None
 
     def warp(self, X):
+        """Beta-CDF warp of X with the current warpers (bask/bayesgpr.py:249-264)."""
+        if self.warp_inputs and hasattr(self, "warpers_"):
+            X = np.asarray(X, dtype=np.float64)
+            X_warped = np.empty_like(X)
+            for col, warper in enumerate(self.warpers_):
+                X_warped[:, col] = warper(X[:, col])
+            X = X_warped
         return X
 
     def unwarp(self, X):
+        """Inverse of ``warp`` (bask/bayesgpr.py:266-283)."""
+        if self.warp_inputs and hasattr(self, "warpers_"):
+            X = np.asarray(X, dtype=np.float64)
+            X_orig = np.empty_like(X)
+            for col, unwarper in enumerate(self.unwarpers_):
+                X_orig[:, col] = unwarper(X[:, col])
+            X = X_orig
         return X
 
     def rewarp(self):
-        pass
+        """Re-applies the warpers to the stored training inputs (bask/bayesgpr.py:285-297)."""
+        self._X_train_warped = None
+
+    def create_warpers(self, alphas, betas):
+        """Beta CDFs / inverse CDFs from log-space parameters (bask/bayesgpr.py:298-316)."""
+        if self.warp_inputs:
+            import scipy.stats as st
+            self.warpers_, self.unwarpers_ = [], []
+            self.warp_alphas_ = np.copy(alphas)
+            self.warp_betas_ = np.copy(betas)
+            for a_log, b_log in zip(alphas, betas, strict=True):
+                dist = st.beta(a=np.exp(a_log), b=np.exp(b_log))
+                self.warpers_.append(dist.cdf)
+                self.unwarpers_.append(dist.ppf)
+            self._X_train_warped = None
 
     @contextmanager
     def noise_set_to_zero(self):
@@ -246,7 +289,7 @@ class BayesGPR:
             self.kernel_.theta = theta
         e = self._eng()
         if not eval_gradient:
-            _, lml, _ = e.logprob(theta[None, :])
+            _, lml, _ = e.logprob(self._theta_for_device(theta)[None, :])
             return float(lml[0])
         h = 1e-5
         p = len(theta)
@@ -254,7 +297,7 @@ class BayesGPR:
         for k in range(p):
             batch[1 + 2 * k, k] += h
             batch[2 + 2 * k, k] -= h
-        _, lml, _ = e.logprob(batch)
+        _, lml, _ = e.logprob(self._theta_for_device(batch))
         if not np.isfinite(lml[0]):
             return -np.inf, np.zeros_like(theta)
         grad = (lml[1::2] - lml[2::2]) / (2 * h)
@@ -287,6 +330,10 @@ class BayesGPR:
                 "Pass X and y, or ensure that you call fit before sample.")
         if priors is None:
             priors = guess_priors(self.kernel_)
+        if warp_priors is None:
+            # Normal(0, 0.3) on log a and log b of every dimension (bask/bayesgpr.py:462-466)
+            from .priors import NormalPrior
+            warp_priors = (NormalPrior(0.0, 0.3), NormalPrior(0.0, 0.3))
         data_changed = False
         if X is not None:
             y = np.asarray(y, dtype=np.float64)
@@ -308,7 +355,7 @@ class BayesGPR:
         if data_changed or noise_vector is not None:
             self._upload_model(structure_changed=False)
 
-        n_dim = len(self.theta)
+        n_dim = n_kernel = len(self.theta)
         if n_walkers is None:
             n_walkers = n_threads * n_walkers_per_thread
         n_samples = int(np.ceil(n_desired_samples / n_walkers) + n_burnin)
@@ -317,9 +364,15 @@ class BayesGPR:
             pos = position
         elif self.pos_ is not None:
             pos = self.pos_
+        added_dims = 0
+        if self.warp_inputs:
+            added_dims = self._X_train.shape[1] * 2
+            n_dim += added_dims
         if pos is None:
             theta = self.theta
             theta[np.isinf(theta)] = np.log(self.noise_)
+            if self.warp_inputs:
+                theta = np.concatenate([theta, np.zeros(added_dims)])
             pos = [theta + 1e-2 * self.random_state.randn(n_dim) for _ in range(n_walkers)]
         pos = np.array(pos, dtype=np.float64)
         if pos.shape != (n_walkers, n_dim):
@@ -340,7 +393,19 @@ class BayesGPR:
                              "are linearly independent for the best performance")
 
         e = self._eng()
-        table, host_fn = as_device_priors(priors, n_dim)
+        table, host_fn = as_device_priors(priors, n_kernel)
+        if self.warp_inputs:
+            # log a_1..a_d then log b_1..b_d follow the kernel's theta (bask/bayesgpr.py:351-365)
+            d_in = added_dims // 2
+            if callable(warp_priors) and not isinstance(warp_priors, (list, tuple)):
+                wtable, wfn = [(_lib.PRIOR_NONE, ())] * added_dims, \
+                    (lambda w, f=warp_priors: float(sum(f(w[k], w[d_in + k]) for k in range(d_in))))
+            else:
+                wtable, wfn = as_device_priors([warp_priors[0]] * d_in + [warp_priors[1]] * d_in, added_dims)
+            table = table + wtable
+            if host_fn is not None or wfn is not None:
+                kf, wf = host_fn, wfn
+                host_fn = lambda th: (kf(th[:n_kernel]) if kf else 0.0) + (wf(th[n_kernel:]) if wf else 0.0)  # noqa: E731
         e.set_priors(table)
         if host_fn is None and process_group is not None and \
                 __import__("torch").distributed.get_world_size(process_group) > 1:
@@ -367,7 +432,12 @@ class BayesGPR:
             self.chain_ = chain
         # point estimate: the factorisation at the geometric median is only enqueued here; its
         # LinAlgError check and the LML read-back happen at the first use (no host round trip)
-        self.kernel_.theta = geometric_median(self.chain_)
+        median = geometric_median(self.chain_)
+        if self.warp_inputs:
+            warp_params = median[n_kernel:]
+            self.create_warpers(warp_params[: added_dims // 2], warp_params[added_dims // 2:])
+            self.rewarp()
+        self.kernel_.theta = median[:n_kernel]
         self._refactor(lazy=True)
         self._lml_from_factor = True
         self.pos_ = pos_out
@@ -389,7 +459,7 @@ class BayesGPR:
         colour = e.empty(W, dtype=torch.int32)
         movers = e.empty(W, dtype=torch.int32)
         q, fac = e.empty(W, p), e.empty(W)
-        acc = torch.zeros(W, dtype=torch.int32, device=e.device)
+        acc = e.zeros(W, dtype=torch.int32)
         chain = e.empty(n_steps, W, p)
         lpc = e.empty(n_steps, W)
         sd = C.c_uint64(seed)
@@ -539,6 +609,8 @@ class BayesGPR:
             raise NotImplementedError("gradient outputs are only used by skopt's own acquisition "
                                       "optimisers and are outside the hot path")
         X = np.asarray(X, dtype=np.float64)
+        if self.warp_inputs:
+            validate_zeroone(X)
         if self.X_train_ is None or self._factor is None:   # GP prior (skopt predict, unfitted branch)
             k = self.kernel if self.kernel is not None else ConstantKernel(1.0) * RBF(1.0)
             y_mean = np.zeros(X.shape[0])
@@ -579,7 +651,8 @@ class BayesGPR:
             _lib.check(e.lib.bgp_posterior_cov(e.h, thetas_dev[s].data_ptr(), v[s].data_ptr(), Xd.data_ptr(), m,
                                                v.shape[2], 0 if noise else 1, y_std, cov.data_ptr(), m, e._st),
                        "bgp_posterior_cov")
-            scale = float(torch.diagonal(cov).abs().max().item()) or 1.0
+            with torch.cuda.stream(e.stream):   # ordered with the kernel that wrote cov
+                scale = float(torch.diagonal(cov).abs().max().item()) or 1.0
             for jit in (1e-10, 1e-9, 1e-8, 1e-7, 1e-6, 1e-5, 1e-4):
                 _lib.check(e.lib.bgp_dense_cholesky(e.h, cov.data_ptr(), m, m, jit * scale, slab.data_ptr(),
                                                     info.data_ptr(), e._st), "bgp_dense_cholesky")

@@ -50,6 +50,7 @@ struct bgp_handle_s {
   DevBuf slabs_scratch;      // one factor slab per resident CTA (logprob mode)
   DevBuf xt_scratch;         // scaled inputs per resident CTA when they exceed shared memory
   DevBuf acq_scratch, extract_scratch;
+  DevBuf warp_x, warp_xc, warp_xt;   // per-theta warped copies of X / candidates / Thompson points
   DevBuf mc_colour, mc_movers, mc_q, mc_factors, mc_newlp, mc_seed;
   uint64_t* seed_pinned = nullptr;
   cudaGraphExec_t graph = nullptr;
@@ -92,7 +93,7 @@ int bgp_destroy(bgp_handle_t h) {
   cudaSetDevice(h->device);
   if (h->graph) cudaGraphExecDestroy(h->graph);
   for (DevBuf* b : {&h->prog, &h->fixed_ls, &h->priors, &h->X, &h->y, &h->alpha, &h->slabs_scratch, &h->xt_scratch,
-                    &h->acq_scratch, &h->extract_scratch, &h->mc_colour, &h->mc_movers, &h->mc_q,
+                    &h->acq_scratch, &h->extract_scratch, &h->warp_x, &h->warp_xc, &h->warp_xt, &h->mc_colour, &h->mc_movers, &h->mc_q,
                     &h->mc_factors, &h->mc_newlp, &h->mc_seed})
     b->release();
   if (h->seed_pinned) cudaFreeHost(h->seed_pinned);
@@ -149,6 +150,34 @@ int bgp_set_kernel(bgp_handle_t h, const bgp_op_t* ops, int n_ops, int n_theta, 
     cudaError_t e = bgp::prepare_chol(h->n);
     if (e != cudaSuccess) return fail("n/d too large for the shared-memory plan of the factorisation kernel", e);
   }
+  return 0;
+}
+
+int bgp_set_warp(bgp_handle_t h, int n_warp) {
+  CHECK_H(h);
+  if (!h->have_prog) return fail("bgp_set_kernel has not been called");
+  if (n_warp < 0 || n_warp > BGP_MAX_DIM) return fail("bad warp dimension count");
+  CUDA_TRY(cudaSetDevice(h->device));
+  DevProgram& P = h->host_prog;
+  const int p_kernel = P.n_warp ? P.warp_off : P.n_theta;
+  if (p_kernel + 2 * n_warp > BGP_MAX_THETA) return fail("too many hyper-parameters with input warping");
+  P.n_warp = n_warp;
+  P.warp_off = p_kernel;
+  P.n_theta = p_kernel + 2 * n_warp;
+  CUDA_TRY(cudaMemcpy(h->prog.p, &P, sizeof(DevProgram), cudaMemcpyHostToDevice));
+  h->have_graph = false;
+  return 0;
+}
+
+// per-theta warped copy of a point set (identity when warping is off: returns the input)
+static int warped(bgp_handle_t h, DevBuf& buf, const double* pts_dev, int npts, const double* theta_dev, int S,
+                  cudaStream_t st, const double** out, long long* stride) {
+  if (h->host_prog.n_warp == 0) { *out = pts_dev; *stride = 0; return 0; }
+  if (h->host_prog.n_warp != h->d) return fail("input warping needs one (a, b) pair per input dimension");
+  CUDA_TRY(buf.ensure(sizeof(double) * (size_t)S * npts * h->d));
+  CUDA_TRY(bgp::launch_warp_points(pts_dev, npts, h->d, theta_dev, S, h->prog.as<DevProgram>(), buf.as<double>(), st));
+  *out = buf.as<double>();
+  *stride = (long long)npts * h->d;
   return 0;
 }
 
@@ -313,7 +342,9 @@ int bgp_predict_batched(bgp_handle_t h, const double* theta_dev, int S, const do
   if (v_dev && (v_ld < 32 * ((h->n + 31) / 32) || (v_ld & 3))) return fail("bad v_ld");
   CUDA_TRY(cudaSetDevice(h->device));
   bgp::SweepArgs A;
-  A.X = h->X.as<double>(); A.theta = theta_dev; A.slabs = slabs_dev; A.z = z_dev; A.Xc = Xc_dev;
+  if (warped(h, h->warp_x, h->X.as<double>(), h->n, theta_dev, S, (cudaStream_t)stream, &A.X, &A.x_stride)) return -1;
+  if (warped(h, h->warp_xc, Xc_dev, m, theta_dev, S, (cudaStream_t)stream, &A.Xc, &A.xc_stride)) return -1;
+  A.theta = theta_dev; A.slabs = slabs_dev; A.z = z_dev;
   A.zextra = zextra_dev; A.mu = mu_dev; A.sd = sd_dev; A.dots = dots_dev; A.v_out = v_dev; A.v_ld = v_ld;
   A.prog = h->prog.as<DevProgram>(); A.fixed_ls = h->fixed_ls.as<double>();
   A.y_mean = y_mean; A.y_std = y_std; A.n = h->n; A.d = h->d; A.S = S; A.m = m; A.R = R;
@@ -413,7 +444,9 @@ int bgp_posterior_cov(bgp_handle_t h, const double* theta_dev, const double* v_d
   if (!theta_dev || !v_dev || !Xc_dev || m <= 0 || !cov_dev || ldc < m || (v_ld & 1)) return fail("bad posterior-cov arguments");
   CUDA_TRY(cudaSetDevice(h->device));
   bgp::PostCovArgs A;
-  A.X = h->X.as<double>(); A.theta = theta_dev; A.v = v_dev; A.Xc = Xc_dev; A.cov = cov_dev; A.v_ld = v_ld;
+  long long unused_stride = 0;
+  if (warped(h, h->warp_xc, Xc_dev, m, theta_dev, 1, (cudaStream_t)stream, &A.Xc, &unused_stride)) return -1;
+  A.X = h->X.as<double>(); A.theta = theta_dev; A.v = v_dev; A.cov = cov_dev; A.v_ld = v_ld;
   A.ldc = ldc; A.prog = h->prog.as<DevProgram>(); A.fixed_ls = h->fixed_ls.as<double>(); A.y_std = y_std;
   A.n = h->n; A.d = h->d; A.m = m; A.noise_off = noise_off;
   CUDA_TRY(bgp::launch_postcov(A, (cudaStream_t)stream));
@@ -454,6 +487,9 @@ int bgp_pvrs_combine(bgp_handle_t h, const double* theta_dev, const double* xt_d
   if (!theta_dev || !xt_dev || R <= 0 || !xc_dev || m <= 0 || !dots_dev || !vt_dev || !s_dev || !out_dev)
     return fail("bad pvrs arguments");
   CUDA_TRY(cudaSetDevice(h->device));
+  long long unused_stride = 0;
+  if (warped(h, h->warp_xt, xt_dev, R, theta_dev, 1, (cudaStream_t)stream, &xt_dev, &unused_stride)) return -1;
+  if (warped(h, h->warp_xc, xc_dev, m, theta_dev, 1, (cudaStream_t)stream, &xc_dev, &unused_stride)) return -1;
   bgp::CombineArgs A{h->prog.as<DevProgram>(), h->fixed_ls.as<double>(), theta_dev, xt_dev, xc_dev, dots_dev,
                      vt_dev, s_dev, nullptr, out_dev, 0, R, m, h->n, h->d};
   CUDA_TRY(bgp::launch_pvrs_combine(A, (cudaStream_t)stream));
@@ -467,6 +503,8 @@ int bgp_vr_combine(bgp_handle_t h, const double* cov_dev, int m, int64_t ldc, co
   if (!cov_dev || m <= 0 || ldc < m || !theta_dev || !s_dev || !out_dev) return fail("bad vr arguments");
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(h->acq_scratch.ensure(sizeof(double) * 64));
+  long long unused_stride = 0;
+  if (xc_dev && warped(h, h->warp_xc, xc_dev, m, theta_dev, 1, (cudaStream_t)stream, &xc_dev, &unused_stride)) return -1;
   bgp::CombineArgs A{h->prog.as<DevProgram>(), h->fixed_ls.as<double>(), theta_dev, nullptr, xc_dev, nullptr,
                      nullptr, s_dev, cov_dev, out_dev, ldc, 0, m, h->n, h->d};
   CUDA_TRY(bgp::launch_vr_combine(A, h->acq_scratch.as<double>(), (cudaStream_t)stream));

@@ -22,9 +22,9 @@ template <int NW>
 struct CholSmem {
   DevProgram prog;
   ThetaParams tp;
-  double Dblk[32 * PS];              // diagonal block being factored
-  double Lt[32 * LS];                // factored block L_kk, DMMA-friendly stride
-  double Wd[4][8 * 8];               // inverses of its four 8x8 diagonal sub-blocks
+  alignas(16) double Dblk[32 * PS];  // diagonal block being factored
+  alignas(16) double Lt[32 * LS];    // factored block L_kk, DMMA-friendly stride
+  alignas(16) double Wd[4][8 * 8];   // inverses of its four 8x8 diagonal sub-blocks
   double red[NW];
   int fail;
 };

@@ -41,9 +41,17 @@ struct DevProgram {
   // fast path for the shape  c * stationary(r) + white  (the default bask kernel): opcode of the
   // stationary leaf (0 = use the interpreter) and the op slots of the constant / white levels
   int fast_kind, fast_const, fast_white, fast_white_zeroable;
+  // input warping (bask warp_inputs=True): theta rows carry 2 * n_warp extra entries after the
+  // kernel's own, log a_1..a_d then log b_1..b_d of the per-dimension Beta CDF warps
+  // (bask/bayesgpr.py:351-365); n_theta is the full row length
+  int n_warp, warp_off;
+  int reserved_[2];   // keeps sizeof(DevProgram) a multiple of 16: shared-memory structs that embed it
+                      // access their later members with 16-byte loads
   bgp_op_t ops[BGP_MAX_OPS];
   int leaf_of_op[BGP_MAX_OPS];
 };
+
+static_assert(sizeof(DevProgram) % 16 == 0, "DevProgram must keep 16-byte alignment of what follows it");
 
 // per-theta resolved parameters (shared memory)
 struct ThetaParams {
@@ -136,6 +144,48 @@ __device__ __forceinline__ double eval_program(const DevProgram& P, const ThetaP
 #undef BGP_PUSH
 #undef BGP_BIN
   return s0;
+}
+
+// -------------------------------------------------------------------------- input warp
+// Regularised incomplete beta function I_x(a, b) = Beta(a, b).cdf(x) (scipy.stats.beta.cdf in
+// bask/bayesgpr.py:298-316): continued fraction (modified Lentz) on the side where it converges
+// fast, prefactor through lgamma.
+__device__ inline double bgp_betacf(double a, double b, double x) {
+  const double TINY = 1e-300, EPS = 1e-16;
+  const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+  double c = 1.0, d = 1.0 - qab * x / qap;
+  if (fabs(d) < TINY) d = TINY;
+  d = 1.0 / d;
+  double h = d;
+  for (int m = 1; m <= 300; ++m) {
+    const double m2 = 2.0 * m;
+    double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+    d = 1.0 + aa * d; if (fabs(d) < TINY) d = TINY;
+    c = 1.0 + aa / c; if (fabs(c) < TINY) c = TINY;
+    d = 1.0 / d;
+    h *= d * c;
+    aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+    d = 1.0 + aa * d; if (fabs(d) < TINY) d = TINY;
+    c = 1.0 + aa / c; if (fabs(c) < TINY) c = TINY;
+    d = 1.0 / d;
+    const double del = d * c;
+    h *= del;
+    if (fabs(del - 1.0) < EPS) break;
+  }
+  return h;
+}
+__device__ inline double bgp_beta_cdf(double x, double a, double b) {
+  if (!(x > 0.0)) return 0.0;
+  if (x >= 1.0) return 1.0;
+  const double front = exp(a * log(x) + b * log1p(-x) - (lgamma(a) + lgamma(b) - lgamma(a + b)));
+  if (x < (a + 1.0) / (a + b + 2.0)) return front * bgp_betacf(a, b, x) / a;
+  return 1.0 - front * bgp_betacf(b, a, 1.0 - x) / b;
+}
+// coordinate kk of a point in the (possibly warped) input space of theta row `theta`
+__device__ __forceinline__ double bgp_warp_coord(const DevProgram& P, const double* __restrict__ theta, int kk,
+                                                 double x) {
+  if (P.n_warp == 0) return x;
+  return bgp_beta_cdf(x, exp(theta[P.warp_off + kk]), exp(theta[P.warp_off + P.n_warp + kk]));
 }
 
 // ------------------------------------------------------------------------------- DMMA

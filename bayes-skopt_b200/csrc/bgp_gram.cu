@@ -33,8 +33,14 @@ __global__ void __launch_bounds__(256) scale_x_kernel(GramArgs A) {
   double* Xt = A.xt + (size_t)b * A.xt_stride;
   for (int e = blockIdx.x * 256 + tid; e < PR.n_leaves * d * npad; e += gridDim.x * 256) {
     const int l = e / (d * npad), rem = e - l * d * npad, kk = rem / npad, i = rem - kk * npad;
-    Xt[e] = (i < A.n) ? A.X[(size_t)i * d + kk] * TP.inv_ls[l][kk] : 0.0;
+    Xt[e] = (i < A.n) ? bgp_warp_coord(PR, A.theta + (size_t)b * PR.n_theta, kk, A.X[(size_t)i * d + kk]) *
+                            TP.inv_ls[l][kk]
+                      : 0.0;
   }
+  // the resolved constants of this theta (exp(theta) per op) follow the scaled inputs, so that the
+  // CTAs of gram_kernel read two doubles instead of resolving theta again
+  if (blockIdx.x == 0 && tid < BGP_MAX_OPS)
+    Xt[(size_t)(PR.n_leaves > 0 ? PR.n_leaves : 1) * d * npad + tid] = tid < PR.n_ops ? TP.opval[tid] : 0.0;
 }
 
 // CTA (32-row chunk of panel k, theta b): 32 x 32 entries of the lower triangle.  A warp takes
@@ -51,14 +57,17 @@ __global__ void __launch_bounds__(256, 6) gram_kernel(GramArgs A) {
   const int b = blockIdx.y, n = A.n, d = A.d;
   int k = 0, chunk = blockIdx.x;
   while (chunk >= gram_chunks(n, k)) { chunk -= gram_chunks(n, k); ++k; }
-  {
+  const int fast_kind = A.prog->fast_kind, n_leaves = A.prog->n_leaves;
+  const double* opv = A.xt + (size_t)b * A.xt_stride + (size_t)(n_leaves > 0 ? n_leaves : 1) * d * gram_nx(n);
+  if (!fast_kind) {
+    // interpreter path: program and resolved constants into shared memory (the length scales are
+    // already folded into Xt)
     const int* src = reinterpret_cast<const int*>(A.prog);
     int* dst = reinterpret_cast<int*>(&PR);
     for (int i = tid; i < (int)(sizeof(DevProgram) / 4); i += 256) dst[i] = src[i];
+    if (tid < BGP_MAX_OPS) TP.opval[tid] = opv[tid];
+    __syncthreads();
   }
-  __syncthreads();
-  resolve_theta(PR, A.theta + (size_t)b * PR.n_theta, A.fixed_ls, TP, tid, 256);
-  __syncthreads();
   const SlabGeom G = SlabGeom::make(n, A.aug != 0);
   const int npad = gram_nx(n);
   const double* Xt = A.xt + (size_t)b * A.xt_stride;
@@ -67,7 +76,7 @@ __global__ void __launch_bounds__(256, 6) gram_kernel(GramArgs A) {
   const int c0 = 32 * k, col = c0 + lane;
   {
     const int r0 = c0 + GRAM_ROWS * chunk + RB * warp;
-    if (PR.fast_kind) {
+    if (fast_kind) {
       double r2[RB];
 #pragma unroll
       for (int a = 0; a < RB; ++a) r2[a] = 0.0;
@@ -87,12 +96,12 @@ __global__ void __launch_bounds__(256, 6) gram_kernel(GramArgs A) {
           r2[2 * a + 1] = fma(t1, t1, r2[2 * a + 1]);
         }
       }
-      const double cval = TP.opval[PR.fast_const], wval = TP.opval[PR.fast_white];
+      const double cval = opv[A.prog->fast_const], wval = opv[A.prog->fast_white];
       double v[RB];
 #pragma unroll
       for (int a = 0; a < RB; ++a) {
         const bool same = (r0 + a) == col;
-        v[a] = cval * stationary_value(PR.fast_kind, same ? 0.0 : r2[a]);
+        v[a] = cval * stationary_value(fast_kind, same ? 0.0 : r2[a]);
         if (same) v[a] += wval + A.alpha[min(r0 + a, n - 1)];
       }
 #pragma unroll
@@ -126,8 +135,28 @@ __global__ void __launch_bounds__(256, 6) gram_kernel(GramArgs A) {
   }
 }
 
+// out[s][i][kk] = warp_{theta_s}(X[i][kk]): the per-theta warped copy of a point set that the
+// sweep / posterior-covariance kernels read instead of the raw points when warping is on
+__global__ void __launch_bounds__(256) warp_points_kernel(const double* __restrict__ X, int npts, int d,
+                                                          const double* __restrict__ theta, const DevProgram* prog,
+                                                          double* __restrict__ out) {
+  const int s = blockIdx.y;
+  const DevProgram& PR = *prog;
+  const double* th = theta + (size_t)s * PR.n_theta;
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < npts * d; e += gridDim.x * 256)
+    out[(size_t)s * npts * d + e] = bgp_warp_coord(PR, th, e % d, X[e]);
+}
+
+cudaError_t launch_warp_points(const double* X, int npts, int d, const double* theta, int S, const DevProgram* prog,
+                               double* out, cudaStream_t stream) {
+  int blocks = (npts * d + 255) / 256;
+  if (blocks > 1024) blocks = 1024;
+  warp_points_kernel<<<dim3(blocks, S), 256, 0, stream>>>(X, npts, d, theta, prog, out);
+  return cudaGetLastError();
+}
+
 size_t gram_xt_doubles(int n, int d, int n_leaves) {
-  return (size_t)(n_leaves > 0 ? n_leaves : 1) * d * gram_nx(n);
+  return (size_t)(n_leaves > 0 ? n_leaves : 1) * d * gram_nx(n) + 32;   // + resolved op constants
 }
 
 cudaError_t launch_gram(const GramArgs& A, cudaStream_t stream) {

@@ -47,6 +47,8 @@ struct GramArgs {
 };
 size_t gram_xt_doubles(int n, int d, int n_leaves);
 cudaError_t launch_gram(const GramArgs& A, cudaStream_t stream);
+cudaError_t launch_warp_points(const double* X, int npts, int d, const double* theta, int S, const DevProgram* prog,
+                               double* out, cudaStream_t stream);
 
 struct SweepArgs {
   const double* X;        // n x d
@@ -54,6 +56,8 @@ struct SweepArgs {
   const double* slabs;    // S factor slabs (aug)
   const double* z;        // S x n
   const double* Xc;       // m x d
+  long long x_stride;     // 0, or n*d / m*d when X / Xc hold one (warped) copy per theta
+  long long xc_stride;
   const double* zextra;   // S x R x n or null
   double* mu;             // S x m
   double* sd;             // S x m

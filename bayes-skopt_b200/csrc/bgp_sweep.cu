@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(SW_NW * 32, 1) sweep_kernel(SweepArgs A) {
   for (int e = tid; e < PR.n_leaves * NC * d; e += SW_NW * 32) {
     int l = e / (NC * d), rem = e - l * NC * d, c = rem / d, kk = rem - c * d;
     int ci = c0 + c;
-    Xs[e] = (ci < A.m) ? A.Xc[(size_t)ci * d + kk] * S.tp.inv_ls[l][kk] : 0.0;
+    Xs[e] = (ci < A.m) ? A.Xc[(size_t)s * A.xc_stride + (size_t)ci * d + kk] * S.tp.inv_ls[l][kk] : 0.0;
   }
   __syncthreads();
   // cross-covariance tile
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(SW_NW * 32, 1) sweep_kernel(SweepArgs A) {
           const double* xc = Xs + (size_t)(l * NC + c) * d;
           double acc = 0.0;
           for (int kk = 0; kk < d; ++kk) {
-            double t = __ldg(A.X + (size_t)i * d + kk) * S.tp.inv_ls[l][kk] - xc[kk];
+            double t = __ldg(A.X + (size_t)s * A.x_stride + (size_t)i * d + kk) * S.tp.inv_ls[l][kk] - xc[kk];
             acc = fma(t, t, acc);
           }
           r2[l] = acc;

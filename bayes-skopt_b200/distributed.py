@@ -205,7 +205,7 @@ def sharded_mcmc(engine, pos, n_steps, seed, a, group, lp_extra_fn=None):
         colour = e.empty(W, dtype=torch.int32)
         movers = e.empty(W, dtype=torch.int32)
         q, fac = e.empty(W, p), e.empty(W)
-        acc = torch.zeros(W, dtype=torch.int32, device=e.device)
+        acc = e.zeros(W, dtype=torch.int32)
         chain = e.empty(n_steps, W, p)
         lpc = e.empty(n_steps, W)
         for t in range(n_steps):

@@ -142,7 +142,12 @@ class Optimizer:
                     self.gp.sample(self.space.transform(self.Xi), self.yi, noise_vector=np.array(self.noisei),
                                    priors=self.gp_priors, n_desired_samples=gp_samples, n_burnin=gp_burnin,
                                    progress=progress)
-            X = self.space.transform(self.space.rvs(n_samples=self.n_points, random_state=self.rng))
+            if self.gp.warp_inputs:
+                # candidates uniform in the warped space, mapped back (bask/optimizer.py:353-357)
+                X_warped = self.rng.uniform(size=(self.n_points, self.space.transformed_n_dims))
+                X = self.gp.unwarp(X_warped)
+            else:
+                X = self.space.transform(self.space.rvs(n_samples=self.n_points, random_state=self.rng))
             acq_values = evaluate_acquisitions(
                 X=X, gpr=self.gp, acquisition_functions=(self.acq_func,), n_samples=n_samples, progress=False,
                 random_state=self.rng.randint(0, np.iinfo(np.int32).max), **self.acq_func_kwargs).flatten()

@@ -83,6 +83,12 @@ int bgp_version(void);
  * (sklearn:_gpr.py:577-586).  fixed_ls: concatenated fixed ARD length scales (may be NULL). */
 int bgp_set_kernel(bgp_handle_t h, const bgp_op_t* ops, int n_ops, int n_theta,
                    const double* fixed_ls, int n_fixed_ls);
+/* warp_inputs=True (bask/bayesgpr.py:219-316, 351-365): every theta row then carries 2*n_warp extra
+ * entries behind the kernel's own -- log a_1..a_d, log b_1..b_d of the per-dimension Beta-CDF
+ * warps -- and every point set (training inputs, candidates) is warped per theta on the device.
+ * n_warp = d enables, 0 disables; call after bgp_set_kernel (which resets it) and before
+ * bgp_set_priors (whose table covers the extended row). */
+int bgp_set_warp(bgp_handle_t h, int n_warp);
 /* priors=None of bask/bayesgpr.py:459-460 -> guess_priors, or the typed user priors. */
 int bgp_set_priors(bgp_handle_t h, const bgp_prior_t* priors, int n_priors);
 /* X_train_/y_train_/alpha of the estimator (bask/bayesgpr.py:469-488).  Copied into the

@@ -343,6 +343,29 @@ def log_prob(spec, theta, X, y, alpha, priors):
     return float(lp)
 
 
+def warp_inputs(X, a_log, b_log):
+    """Beta-CDF warp of every input dimension (bask/bayesgpr.py:249-264, 298-316): column k is
+    mapped through scipy.stats.beta(exp(a_log[k]), exp(b_log[k])).cdf."""
+    import scipy.stats as st
+    X = np.asarray(X, dtype=np.float64)
+    out = np.empty_like(X)
+    for k in range(X.shape[1]):
+        out[:, k] = st.beta(a=np.exp(a_log[k]), b=np.exp(b_log[k])).cdf(X[:, k])
+    return out
+
+
+def log_prob_warped(spec, theta_full, X, y, alpha, priors, warp_priors):
+    """bask/bayesgpr.py:351-379 with warp_inputs=True: theta_full = kernel theta ++ log a ++ log b;
+    warp_priors is the (prior_a, prior_b) pair applied per dimension."""
+    d = X.shape[1]
+    theta_full = np.asarray(theta_full, dtype=np.float64)
+    x_gp, a_log, b_log = theta_full[:-2 * d], theta_full[-2 * d:-d], theta_full[-d:]
+    lp = 0
+    for a, b in zip(a_log, b_log):
+        lp += warp_priors[0](a) + warp_priors[1](b)
+    return lp + log_prob(spec, x_gp, warp_inputs(X, a_log, b_log), y, alpha, priors) if np.isfinite(lp) else -np.inf
+
+
 def factorize(spec, theta, X, y, alpha):
     """bask/bayesgpr.py:200-217: L_, K_inv_ = L^-T L^-1, alpha_ = K^-1 y."""
     K = gram(spec, theta, X, alpha)

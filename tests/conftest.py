@@ -44,3 +44,8 @@ def g4():
 @pytest.fixture(scope="session")
 def g5():
     return load_golden("g5_branin_long_chain.npz")
+
+
+@pytest.fixture(scope="session")
+def g6():
+    return load_golden("g6_branin_warp.npz")

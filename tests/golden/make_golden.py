@@ -209,8 +209,66 @@ def g5():
     np.savez_compressed(os.path.join(HERE, "g5_branin_long_chain.npz"), **d)
 
 
+def g6():
+    """Input warping (warp_inputs=True) on config 1: log-posterior / LML at full
+    theta rows (kernel theta ++ log a ++ log b), predictions and a swept EI / LCB / MES with the
+    per-theta warps, the fitted point estimate and its warp parameters."""
+    print("G6: config 1 with warp_inputs=True")
+    import scipy.stats as st
+    w = W.config1()
+    gp = BayesGPR(kernel=construct_default_kernel(list(range(w.d))), normalize_y=True, warp_inputs=True,
+                  random_state=3)
+    gp.fit(w.X, w.y, noise_vector=w.noise_vector, n_desired_samples=w.n_desired_samples, n_burnin=w.n_burnin,
+           n_walkers_per_thread=w.n_walkers, progress=False)
+    d = dict(X=w.X, y_raw=w.y, noise_vector=w.noise_vector, y_train=gp.y_train_,
+             y_mean=np.atleast_1d(gp.y_train_mean_), y_std=np.atleast_1d(gp.y_train_std_),
+             alpha_vec=np.asarray(gp.alpha, dtype=np.float64) * np.ones(w.n),
+             chain=gp.chain_, pos=np.asarray(gp.pos_), theta_median=gp.theta,
+             warp_alphas=gp.warp_alphas_.copy(), warp_betas=gp.warp_betas_.copy(),
+             lml_at_median=np.atleast_1d(gp.log_marginal_likelihood_value_), noise_=np.atleast_1d(gp.noise_),
+             Xc=w.candidates, X_train_warped=gp.X_train_.copy())
+    priors = guess_priors(gp.kernel_)
+    wp = (st.norm(loc=0.0, scale=0.3).logpdf, st.norm(loc=0.0, scale=0.3).logpdf)
+    a_bak, b_bak, th_bak = gp.warp_alphas_.copy(), gp.warp_betas_.copy(), gp.theta
+    # a spread of full rows: chain rows and exaggerated warps
+    rows = gp.chain_[:12].copy()
+    rs = np.random.RandomState(9)
+    big = gp.chain_[12:16].copy()
+    big[:, -2 * w.d:] = rs.uniform(-1.2, 1.2, size=(4, 2 * w.d))
+    rows = np.vstack([rows, big])
+    d["thetas"] = rows
+    d["logprob"] = np.array([gp._log_prob_fn(t, priors=priors, warp_priors=wp) for t in rows])
+    lml, mus, stds = [], [], []
+    nk = len(th_bak)
+    for t in rows:
+        gp.create_warpers(t[nk:nk + w.d], t[nk + w.d:])
+        gp.rewarp()
+        lml.append(gp.log_marginal_likelihood(t[:nk]))
+        gp.theta = t[:nk]
+        with gp.noise_set_to_zero():
+            mu, std = gp.predict(w.candidates, return_std=True)
+        mus.append(mu)
+        stds.append(std)
+    d.update(lml=np.array(lml), mu=np.array(mus), std=np.array(stds))
+    gp.create_warpers(a_bak, b_bak)
+    gp.rewarp()
+    gp.theta = th_bak
+    d["mu_median"], d["std_median"] = gp.predict(w.candidates, return_std=True)
+    d["warp_of_Xc"] = gp.warp(w.candidates)
+    d["unwarp_roundtrip"] = gp.unwarp(gp.warp(w.candidates[:50]))
+    d.update(sweep_vectors(gp, w.candidates, [ExpectedImprovement(), LCB(), MaxValueSearch()],
+                           ["ei", "lcb", "mes"], 10, 1, w.mes_seed))
+    d["vr"] = VarianceReduction()(w.candidates[:100], gp)
+    d["pvrs"] = PVRS()(w.candidates, gp, n_thompson=10, random_state=np.random.RandomState(5))
+    rs5 = np.random.RandomState(5)
+    ts = gp.sample_y(gp.warp(w.candidates) if False else w.candidates, sample_mean=True, n_samples=10,
+                     random_state=rs5)
+    d["pvrs_thompson_idx"] = np.argmin(ts, axis=0).astype(np.int64)
+    np.savez_compressed(os.path.join(HERE, "g6_branin_warp.npz"), **d)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["g1", "g2", "g3", "g4", "g5"]
+    which = sys.argv[1:] or ["g1", "g2", "g3", "g4", "g5", "g6"]
     for name in which:
         globals()[name]()
     for f in sorted(os.listdir(HERE)):

@@ -114,8 +114,8 @@ def test_estimator_argument_errors():
     gp = bask_b200.BayesGPR(kernel=bask_b200.construct_default_kernel([0]))
     with pytest.raises(ValueError):
         gp.sample()
-    with pytest.raises(NotImplementedError):
-        bask_b200.BayesGPR(warp_inputs=True)
+    gw = bask_b200.BayesGPR(warp_inputs=True)      # input warping: identity until warpers exist
+    assert gw.warp_inputs and gw.warp(np.ones((1, 1)))[0, 0] == 1.0
     assert gp.theta is None and gp.chain_ is None and gp.pos_ is None
     mu, sd = gp.predict(np.zeros((2, 1)), return_std=True)    # GP prior before any fit
     np.testing.assert_allclose(mu, 0.0)

@@ -143,3 +143,27 @@ def test_known_answer_priors():
     for p, v in zip(pr, [-0.02116327824572739, -2.112906921232193, -0.02116327824572739,
                          -0.02116327824572739]):
         assert abs(p(-0.9) - v) < 1e-7
+
+
+def test_warped_log_prob(g6):
+    """Input warping: oracle log-posterior / LML / predictions at full theta rows
+    (kernel theta ++ log a ++ log b) against the reference with warp_inputs=True."""
+    import scipy.stats as st
+    g, d = g6, 2
+    spec = default_spec(d)
+    priors = G.guess_priors(spec)
+    wp = (st.norm(loc=0.0, scale=0.3).logpdf, st.norm(loc=0.0, scale=0.3).logpdf)
+    lp = [G.log_prob_warped(spec, t, g["X"], g["y_train"], g["alpha_vec"], priors, wp) for t in g["thetas"]]
+    np.testing.assert_allclose(lp, g["logprob"], rtol=RTOL)
+    for s in (0, 13):
+        t = g["thetas"][s]
+        Xw = G.warp_inputs(g["X"], t[-2 * d:-d], t[-d:])
+        lml = G.log_marginal_likelihood(spec, t[:-2 * d], Xw, g["y_train"], g["alpha_vec"])
+        np.testing.assert_allclose(lml, g["lml"][s], rtol=RTOL)
+        L, K_inv, a = G.factorize(spec, t[:-2 * d], Xw, g["y_train"], g["alpha_vec"])
+        mu, std = G.predict(spec, t[:-2 * d], Xw, G.warp_inputs(g["Xc"], t[-2 * d:-d], t[-d:]), K_inv, a,
+                            float(g["y_mean"][0]), float(g["y_std"][0]))
+        np.testing.assert_allclose(mu, g["mu"][s], rtol=RTOL, atol=1e-12)
+        np.testing.assert_allclose(std, g["std"][s], rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(G.warp_inputs(g["X"], g["warp_alphas"], g["warp_betas"]), g["X_train_warped"],
+                               rtol=1e-12)
