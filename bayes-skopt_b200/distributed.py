@@ -229,6 +229,10 @@ def sharded_mcmc(engine, pos, n_steps, seed, a, group, lp_extra_fn=None):
 def _allgather_1d(t, sizes, group):
     """ragged all-gather of 1-D tensors (sizes[r] elements from rank r) -> concatenation"""
     mmax = max(sizes)
+    if min(sizes) == mmax:     # equal shards (the usual case): one collective straight into the result
+        out = torch.empty(mmax * len(sizes), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+        return out
     pad = torch.zeros(mmax, dtype=t.dtype, device=t.device)
     pad[: t.shape[0]] = t
     parts = [torch.empty_like(pad) for _ in sizes]

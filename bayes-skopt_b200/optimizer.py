@@ -13,7 +13,8 @@ from sklearn.utils import check_random_state
 from . import acquisition
 from .acquisition import evaluate_acquisitions
 from .bayesgpr import BayesGPR
-from .space import create_result, is_2Dlistlike, is_listlike, normalize_dimensions
+from .space import (create_result, expected_minimum, hdi, is_2Dlistlike, is_listlike,
+                    normalize_dimensions)
 from .utils import construct_default_kernel
 
 __all__ = ["Optimizer", "r2_sequence"]
@@ -168,3 +169,94 @@ class Optimizer:
                       gp_burnin=gp_burnin, replace=replace)
             replace = False
         return create_result(self.Xi, self.yi, self.space, self.rng, models=[self.gp])
+
+    # ------------------------------------------------------------------ diagnostics
+    def _expected_optimum(self, n_random_starts, random_state):
+        """expected_minimum of the current surrogate; identical calls (same data, same integer
+        seed -- what expected_optimality_gap issues dozens of times) are answered from a cache."""
+        key = None
+        if isinstance(random_state, (int, np.integer)):
+            key = (len(self.Xi), id(self.gp.chain_), int(random_state), int(n_random_starts))
+            if getattr(self, "_expected_optimum_cache", (None, None))[0] == key:
+                return self._expected_optimum_cache[1]
+        result = create_result(self.Xi, self.yi, self.space, self.rng, models=[self.gp])
+        x = expected_minimum(result, random_state=random_state, n_random_starts=n_random_starts)[0]
+        if key is not None:
+            self._expected_optimum_cache = (key, x)
+        return x
+
+    def probability_of_optimality(self, threshold, n_space_samples=500, n_gp_samples=200, n_random_starts=100,
+                                  use_mean_gp=True, normalized_scores=True, random_state=None):
+        """Probability that the current expected optimum cannot be improved by more than
+        ``threshold`` (float or list), from joint posterior draws over the optimum and
+        ``n_space_samples`` random points (bask/optimizer.py:447-525).  The draws come from the
+        device ``sample_y`` (Cholesky instead of numpy's SVD: same distribution, other variates)."""
+        X_orig = [self._expected_optimum(n_random_starts, random_state)]
+        X_orig.extend(self.space.rvs(n_samples=n_space_samples, random_state=random_state))
+        X_trans = self.space.transform(X_orig)
+        score_samples = self.gp.sample_y(X_trans, n_samples=n_gp_samples, sample_mean=use_mean_gp,
+                                         random_state=random_state)
+        if normalized_scores:
+            std = np.std(score_samples, axis=0)
+        if not is_listlike(threshold):
+            threshold = [threshold]
+        probabilities = []
+        for eps in threshold:
+            if normalized_scores:
+                diff = (score_samples[0][None, :] - score_samples) / std
+            else:
+                diff = score_samples[0][None, :] - score_samples
+            probabilities.append(((diff - eps).max(axis=0) < 0.0).mean())
+        if len(probabilities) == 1:
+            return probabilities[0]
+        return probabilities
+
+    def expected_optimality_gap(self, max_tries=3, n_probabilities=50, n_space_samples=500, n_gp_samples=200,
+                                n_random_starts=100, tol=0.01, use_mean_gp=True, normalized_scores=True,
+                                random_state=None):
+        """Expected optimality gap of the current optimum w.r.t. sampled consistent optima
+        (bask/optimizer.py:527-620)."""
+        from scipy.optimize import minimize_scalar
+        random_state = check_random_state(random_state)
+        seed = random_state.randint(0, 2 ** 32 - 1, dtype=np.int64)
+        kw = dict(n_random_starts=n_random_starts, n_gp_samples=n_gp_samples, n_space_samples=n_space_samples,
+                  use_mean_gp=use_mean_gp, normalized_scores=normalized_scores, random_state=seed)
+
+        def func(threshold):
+            prob = self.probability_of_optimality(threshold=threshold, **kw)
+            return (prob - 1.0) ** 2 + threshold ** 2 * 1e-3
+
+        max_observed_gap = np.max(self.yi) - np.min(self.yi)
+        for _ in range(max_tries):
+            try:
+                upper_threshold = minimize_scalar(func, bounds=(0.0, max_observed_gap), tol=tol).x
+                break
+            except ValueError:
+                pass
+        else:
+            raise ValueError("Determining the upper threshold was not possible.")
+        thresholds = list(np.linspace(0, upper_threshold, num=n_probabilities))
+        probabilities = self.probability_of_optimality(thresholds, **kw)
+        expected_gap = 0.0
+        for i in range(0, len(probabilities) - 1):
+            p = probabilities[i + 1] - probabilities[i]
+            expected_gap += p * thresholds[i + 1]
+        return expected_gap
+
+    def optimum_intervals(self, hdi_prob=0.95, multimodal=True, opt_samples=200, space_samples=500,
+                          only_mean=True, random_state=None):
+        """Highest density intervals of the optimum's location per dimension, from Thompson
+        samples of the optimum (bask/optimizer.py:622-689).  Returns a list of (n_modes, 2)
+        arrays in the original space."""
+        if self.space.is_partly_categorical:
+            raise NotImplementedError("Highest density interval not implemented for categorical parameters.")
+        X = self.space.rvs(n_samples=space_samples, random_state=random_state)
+        X = self.space.transform(X)
+        optimum_samples = self.gp.sample_y(X, sample_mean=only_mean, n_samples=opt_samples,
+                                           random_state=random_state)
+        X_opt = X[np.argmin(optimum_samples, axis=0)]
+        intervals = []
+        for i, col in enumerate(X_opt.T):
+            raw_interval = hdi(col, hdi_prob=hdi_prob, multimodal=multimodal)
+            intervals.append(np.asarray(self.space.dimensions[i].inverse_transform(raw_interval)))
+        return intervals

@@ -8,7 +8,7 @@ import numpy as np
 from scipy.optimize import OptimizeResult
 from sklearn.utils import check_random_state
 
-__all__ = ["Real", "Integer", "Categorical", "Space", "normalize_dimensions", "create_result",
+__all__ = ["Real", "Integer", "Categorical", "Space", "normalize_dimensions", "create_result", "expected_minimum", "hdi",
            "is_listlike", "is_2Dlistlike"]
 
 _ONE_PLUS = np.nextafter(1.0, 2.0)
@@ -174,3 +174,54 @@ def create_result(Xi, yi, space=None, rng=None, specs=None, models=None):
     res.random_state = rng
     res.specs = specs
     return res
+
+
+def expected_minimum(res, n_random_starts=20, random_state=None):
+    """Minimum of the surrogate mean (skopt.utils.expected_minimum as used by
+    bask/optimizer.py:490-504): L-BFGS-B on ``res.models[-1].predict`` in the original space, started
+    from the best observed point and ``n_random_starts`` random points.  Returns ``(x, fun)``."""
+    from scipy.optimize import minimize
+
+    def func(x):
+        xt = res.space.transform(np.asarray(x).reshape(1, -1))
+        return float(res.models[-1].predict(xt.reshape(1, -1))[0])
+
+    xs = [res.x]
+    if n_random_starts > 0:
+        xs.extend(res.space.rvs(n_random_starts, random_state=random_state))
+    best_x, best_fun = None, np.inf
+    for x0 in xs:
+        r = minimize(func, x0=x0, bounds=res.space.bounds)
+        if r.fun < best_fun:
+            best_x, best_fun = r.x, r.fun
+    return [v for v in best_x], best_fun
+
+
+def hdi(x, hdi_prob=0.95, multimodal=False):
+    """Highest density interval(s) of a 1-D sample (the role arviz.hdi plays in
+    bask/optimizer.py:681-689).  Unimodal: the shortest interval holding ``hdi_prob`` of the
+    sample, shape (2,).  Multimodal: the region where a Gaussian KDE exceeds the density level that
+    encloses ``hdi_prob`` of its mass, as an (n_modes, 2) array."""
+    x = np.sort(np.asarray(x, dtype=np.float64).ravel())
+    n = len(x)
+    if n == 0:
+        raise ValueError("hdi needs at least one sample")
+    if not multimodal or n < 3 or x[0] == x[-1]:
+        inc = int(np.floor(hdi_prob * n))
+        n_intervals = n - inc
+        if n_intervals < 1 or inc < 1:
+            return np.array([x[0], x[-1]])
+        widths = x[inc:] - x[:n_intervals]
+        i = int(np.argmin(widths))
+        out = np.array([x[i], x[i + inc]])
+        return out[None, :] if multimodal else out
+    from scipy.stats import gaussian_kde
+    grid = np.linspace(x[0], x[-1], 512)
+    dens = gaussian_kde(x)(grid)
+    dens = dens / dens.sum()
+    order = np.argsort(dens)[::-1]
+    k = int(np.searchsorted(np.cumsum(dens[order]), hdi_prob)) + 1
+    inside = np.zeros(len(grid), dtype=bool)
+    inside[order[:k]] = True
+    edges = np.flatnonzero(np.diff(np.concatenate([[0], inside.astype(np.int8), [0]])))
+    return np.array([[grid[a], grid[b - 1]] for a, b in zip(edges[::2], edges[1::2])])

@@ -1,0 +1,43 @@
+"""CPU: host-side pieces of the optimiser diagnostics: expected_minimum and hdi.
+The reference takes both from third-party packages (skopt.utils.expected_minimum, arviz.hdi)."""
+import numpy as np
+
+import bask_b200.space as S
+
+
+class _Bowl:
+    def predict(self, X):
+        return np.array([((X[0, 0] - 0.3) ** 2 + (X[0, 1] - 0.6) ** 2)])
+
+
+def test_expected_minimum_finds_the_surrogate_minimum():
+    sp = S.normalize_dimensions([(-2.0, 3.0), (0.0, 10.0)])
+    res = S.create_result([[0.0, 1.0], [1.0, 5.0]], [1.0, 0.5], sp, np.random.RandomState(0), models=[_Bowl()])
+    x, fun = S.expected_minimum(res, n_random_starts=5, random_state=0)
+    np.testing.assert_allclose(x, [-2.0 + 0.3 * 5.0, 0.6 * 10.0], atol=1e-4)     # minimum in the original space
+    assert fun < 1e-8
+    # same oracle restatement (App. A3 of SURVEY.md): identical starts, identical answer
+    from oracle import skopt_port
+    sp2 = skopt_port.normalize_dimensions([(-2.0, 3.0), (0.0, 10.0)])
+    res2 = skopt_port.create_result([[0.0, 1.0], [1.0, 5.0]], [1.0, 0.5], sp2, np.random.RandomState(0),
+                                    models=[_Bowl()])
+    x2, fun2 = skopt_port.expected_minimum(res2, n_random_starts=5, random_state=0)
+    np.testing.assert_allclose(x, x2, rtol=1e-12)
+    np.testing.assert_allclose(fun, fun2, atol=1e-15)
+
+
+def test_hdi_unimodal_and_multimodal():
+    rs = np.random.RandomState(0)
+    x = rs.randn(20000)
+    lo, hi = S.hdi(x, 0.95)
+    assert abs(lo + 1.96) < 0.08 and abs(hi - 1.96) < 0.08
+    # shortest interval: no other window with the same number of samples is shorter
+    xs = np.sort(x)
+    inc = int(np.floor(0.95 * len(xs)))
+    assert hi - lo <= np.min(xs[inc:] - xs[: len(xs) - inc]) + 1e-12
+    two = np.concatenate([rs.randn(5000) * 0.1 - 2, rs.randn(5000) * 0.1 + 2])
+    modes = S.hdi(two, 0.9, multimodal=True)
+    assert modes.shape == (2, 2) and modes[0, 1] < 0 < modes[1, 0]
+    one = S.hdi(x, 0.95, multimodal=True)
+    assert one.shape == (1, 2)
+    assert S.hdi(np.array([0.5]), 0.95).tolist() == [0.5, 0.5]

@@ -220,3 +220,32 @@ def test_optimizer_every_acquisition(bask, acq):
     opt.tell([0.5, 0.5], f([0.5, 0.5]), n_samples=2, gp_samples=100, gp_burnin=2)
     nxt = opt.ask()
     assert len(nxt) == 2 and all(0.0 <= v <= 1.0 for v in nxt)
+
+
+def test_optimizer_diagnostics(bask):
+    """probability_of_optimality / expected_optimality_gap / optimum_intervals on a
+    fitted optimiser: the joint draws are device draws, so the checks are distributional."""
+    opt = bask.Optimizer(dimensions=[(-2.0, 2.0), (-2.0, 2.0)], n_points=300, n_initial_points=12, acq_func="mes",
+                         random_state=0)
+    f = lambda x: (x[0] - 0.5) ** 2 + (x[1] + 0.5) ** 2   # noqa: E731
+    for i in range(12):
+        x = opt.ask()
+        opt.tell(x, f(x), fit=(i == 11), n_samples=2, gp_samples=100, gp_burnin=5)
+    for _ in range(6):
+        x = opt.ask()
+        opt.tell(x, f(x), n_samples=2, gp_samples=100, gp_burnin=5)
+    probs = opt.probability_of_optimality([0.0, 0.5, 2.0, 8.0], n_space_samples=200, n_gp_samples=100,
+                                          n_random_starts=5, random_state=0)
+    assert len(probs) == 4 and all(0.0 <= p <= 1.0 for p in probs)
+    assert all(b >= a for a, b in zip(probs, probs[1:])) and probs[-1] > 0.9
+    single = opt.probability_of_optimality(8.0, n_space_samples=200, n_gp_samples=100, n_random_starts=5,
+                                           random_state=0)
+    assert single == probs[-1]                      # same seed, same draws
+    gap = opt.expected_optimality_gap(n_probabilities=20, n_space_samples=150, n_gp_samples=60, n_random_starts=3,
+                                      random_state=0)
+    assert np.isfinite(gap) and 0.0 <= gap < np.max(opt.yi) - np.min(opt.yi)
+    iv = opt.optimum_intervals(hdi_prob=0.9, opt_samples=100, space_samples=300, random_state=0)
+    assert len(iv) == 2 and all(a.ndim == 2 and a.shape[1] == 2 for a in iv)
+    assert iv[0][:, 0].min() <= 0.5 + 0.8 and iv[0][:, 1].max() >= 0.5 - 0.8
+    uni = opt.optimum_intervals(hdi_prob=0.9, multimodal=False, opt_samples=100, space_samples=300, random_state=0)
+    assert all(np.asarray(a).shape == (2,) and a[0] <= a[1] for a in uni)

@@ -16,4 +16,4 @@ for i in range(3): cycle(i)
 pr = cProfile.Profile(); pr.enable()
 for i in range(10): cycle(10 + i)
 pr.disable()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(32)
+pstats.Stats(pr).sort_stats("tottime").print_stats(28)
