@@ -50,10 +50,46 @@ def r2_sequence(n, d, seed=0.5):
     return (seed + alpha[None, :] * (np.arange(n)[:, None] + 1)) % 1
 
 
+def _sb_energy(x, pts):
+    """Steinerberger's energy of a trial point against the points placed so far:
+    sum_j prod_k (1 - log(2 sin(pi |x_k - p_jk|))); +inf when the trial point sits on one of them."""
+    diff = np.abs(np.asarray(x)[None, :] - pts)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        terms = 1.0 - np.log(2.0 * np.sin(np.pi * diff))
+    val = np.sum(np.prod(terms, axis=-1))
+    return val if np.isfinite(val) else np.inf
+
+
+def sb_sequence(n, d, existing_points=None, random_state=None, restarts=20):
+    """Greedy low-discrepancy sequence of Steinerberger (2019) in [0, 1]^d, the reference's
+    ``init_strategy="sb"`` (bask/init.py:26-100): every new point minimises the energy above,
+    searched by L-BFGS-B from ``restarts`` uniform starting points.  Consumes ``random_state`` in
+    the reference's order (one uniform(d) for the first point when nothing exists, then one
+    uniform((restarts, d)) block per added point).  Host-only: it runs before any GP exists."""
+    from scipy.optimize import minimize
+    rng = check_random_state(random_state)
+    if existing_points is None:
+        pts = [rng.uniform(size=d)]
+    else:
+        pts = [np.asarray(p, dtype=np.float64) for p in existing_points]
+        if len(pts) >= n:
+            raise ValueError("No more points left to generate.")
+    for _ in range(n - len(pts)):
+        starts = rng.uniform(size=(restarts, d))
+        best_val, best_pt = np.inf, starts[0]
+        placed = np.array(pts)
+        for x0 in starts:
+            with np.errstate(invalid="ignore"):
+                res = minimize(_sb_energy, x0=x0, bounds=[(0.0, 1.0)] * d, args=(placed,))
+            if res.fun < best_val:
+                best_val, best_pt = res.fun, res.x
+        pts.append(best_pt)
+    return np.array(pts)
+
+
 class Optimizer:
     """Stepwise Bayesian optimisation with a fully Bayesian GP (see bask/optimizer.py:35-119 for
-    the parameters).  ``init_strategy="sb"`` is served by the R2 sequence here (the
-    Steinerberger design runs only before any GP exists and is outside the hot path)."""
+    the parameters)."""
 
     def __init__(self, dimensions, n_points=500, n_initial_points=10, init_strategy="sb", gp_kernel=None,
                  gp_kwargs=None, gp_priors=None, acq_func="pvrs", acq_func_kwargs=None, random_state=None,
@@ -70,11 +106,11 @@ class Optimizer:
         self._n_initial_points = n_initial_points
         self.n_initial_points_ = n_initial_points
         self.init_strategy = init_strategy
-        if self.init_strategy in ("r2", "sb"):
-            if self.init_strategy == "sb":
-                self._init_rng = np.random.RandomState(self.rng.randint(2 ** 31))
+        if self.init_strategy == "r2":
             self._initial_points = self.space.inverse_transform(
                 r2_sequence(n=max(n_initial_points, 1), d=self.space.n_dims))
+        elif self.init_strategy == "sb":
+            self._init_rng = np.random.RandomState(self.rng.randint(2 ** 31))
         self.n_points = n_points
         if gp_kwargs is None:
             gp_kwargs = {}
@@ -93,8 +129,13 @@ class Optimizer:
         if n_points > 1:
             raise NotImplementedError("Returning multiple points is not implemented yet.")
         if self._n_initial_points > 0:
-            if self.init_strategy in ("r2", "sb"):
+            if self.init_strategy == "r2":
                 return self._initial_points[self._n_initial_points - 1]
+            if self.init_strategy == "sb":
+                existing = self.space.transform(self.Xi) if len(self.Xi) > 0 else None
+                points = sb_sequence(n=len(self.Xi) + 1, d=self.space.transformed_n_dims,
+                                     existing_points=existing, random_state=self._init_rng.randint(2 ** 31))
+                return self.space.inverse_transform(np.atleast_2d(points[len(self.Xi)]))[0]
             return self.space.rvs()[0]
         if not self.gp.kernel_:
             raise RuntimeError("Initialization is finished, but no model has been fit.")

@@ -41,3 +41,27 @@ def test_hdi_unimodal_and_multimodal():
     one = S.hdi(x, 0.95, multimodal=True)
     assert one.shape == (1, 2)
     assert S.hdi(np.array([0.5]), 0.95).tolist() == [0.5, 0.5]
+
+
+def test_sb_sequence_matches_reference():
+    """Steinerberger initial design: same points as the reference's sb_sequence for
+    the same RandomState (checked against the unmodified reference when it is available, i.e. in
+    the build container; structural checks everywhere)."""
+    import os
+
+    import bask_b200
+    pts = bask_b200.sb_sequence(6, 2, random_state=3, restarts=5)
+    assert pts.shape == (6, 2) and np.all((pts >= 0) & (pts <= 1))
+    d = np.abs(pts[:, None, :] - pts[None, :, :]).sum(-1)
+    assert np.min(d[np.triu_indices(6, 1)]) > 0.05                 # well separated
+    more = bask_b200.sb_sequence(8, 2, existing_points=pts, random_state=4, restarts=5)
+    np.testing.assert_array_equal(more[:6], pts)
+    with np.testing.assert_raises(ValueError):
+        bask_b200.sb_sequence(6, 2, existing_points=pts)
+    if os.path.isdir("/root/reference/bask"):
+        from oracle.ref_loader import load_reference
+        load_reference()
+        from bask.init import sb_sequence as ref_sb
+        np.testing.assert_allclose(pts, ref_sb(6, 2, random_state=3, restarts=5), rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(more, ref_sb(8, 2, existing_points=pts, random_state=4, restarts=5),
+                                   rtol=1e-9, atol=1e-12)
