@@ -35,6 +35,7 @@ _SIGNATURES = {
     "bgp_version": [],
     "bgp_set_kernel": [_P, C.POINTER(Op), C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int],
     "bgp_set_warp": [_P, C.c_int],
+    "bgp_mcmc_seed_source": [_P, _P],
     "bgp_set_priors": [_P, C.POINTER(Prior), C.c_int],
     "bgp_set_data": [_P, _P, _P, _P, C.c_int, C.c_int, _P],
     "bgp_logprob_batched": [_P, _P, C.c_int, _P, _P, _P, _P, _P],

@@ -56,6 +56,7 @@ struct bgp_handle_s {
   cudaGraphExec_t graph = nullptr;
   GraphKey key;
   bool have_graph = false;
+  const uint64_t* step_seed_dev = nullptr;   // stepped MCMC entry points: seed read from here when set
   long long* dbg = nullptr;   // developer tooling: clock stamps of the factorisation kernel
   int dbg_tid = 0;
 };
@@ -515,7 +516,7 @@ int bgp_mcmc_split(bgp_handle_t h, int W, uint64_t seed, int step, int32_t* colo
   CHECK_H(h);
   if (W < 2 || W > 8192 || !colour_dev) return fail("bad split arguments");
   CUDA_TRY(cudaSetDevice(h->device));
-  CUDA_TRY(bgp::launch_split(W, seed, nullptr, step, colour_dev, (cudaStream_t)stream));
+  CUDA_TRY(bgp::launch_split(W, seed, h->step_seed_dev, step, colour_dev, (cudaStream_t)stream));
   return 0;
 }
 
@@ -527,7 +528,7 @@ int bgp_mcmc_propose(bgp_handle_t h, const double* pos_dev, const int32_t* colou
   if (!pos_dev || !colour_dev || W < 2 || W > 8192 || !q_dev || !factors_dev || !movers_dev)
     return fail("bad propose arguments");
   CUDA_TRY(cudaSetDevice(h->device));
-  CUDA_TRY(bgp::launch_propose(pos_dev, colour_dev, W, h->host_prog.n_theta, half, a, seed, nullptr, step,
+  CUDA_TRY(bgp::launch_propose(pos_dev, colour_dev, W, h->host_prog.n_theta, half, a, seed, h->step_seed_dev, step,
                                q_dev, factors_dev, movers_dev, (cudaStream_t)stream));
   return 0;
 }
@@ -541,8 +542,14 @@ int bgp_mcmc_accept(bgp_handle_t h, double* pos_dev, double* lp_dev, const doubl
   if (!pos_dev || !lp_dev || !q_dev || !factors_dev || !new_lp_dev || !movers_dev) return fail("bad accept arguments");
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(bgp::launch_accept(pos_dev, lp_dev, q_dev, factors_dev, new_lp_dev, movers_dev, W,
-                              h->host_prog.n_theta, half, seed, nullptr, step, accepted_dev, chain_step_dev,
+                              h->host_prog.n_theta, half, seed, h->step_seed_dev, step, accepted_dev, chain_step_dev,
                               lp_step_dev, (cudaStream_t)stream));
+  return 0;
+}
+
+int bgp_mcmc_seed_source(bgp_handle_t h, const uint64_t* seed_dev) {
+  CHECK_H(h);
+  h->step_seed_dev = seed_dev;
   return 0;
 }
 

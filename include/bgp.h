@@ -223,6 +223,11 @@ int bgp_mcmc_accept(bgp_handle_t h, double* pos_dev, double* lp_dev, const doubl
                     const int32_t* movers_dev, int W, int half, uint64_t seed, int step,
                     int32_t* accepted_dev, double* chain_step_dev, double* lp_step_dev,
                     void* stream);
+/* Stepped entry points above: when seed_dev is not NULL the Philox key is read from that device
+ * word instead of the by-value `seed` argument, so a caller can capture the stepped loop (with its
+ * own collectives between propose and accept) in a CUDA graph and replay it with a new seed.
+ * NULL restores by-value seeds. */
+int bgp_mcmc_seed_source(bgp_handle_t h, const uint64_t* seed_dev);
 
 #ifdef __cplusplus
 }
