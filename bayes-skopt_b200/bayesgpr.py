@@ -304,12 +304,35 @@ class BayesGPR:
         grad[~np.isfinite(grad)] = 0.0
         return float(lml[0]), grad
 
+    def _prior_table(self, priors, warp_priors, n_kernel):
+        """(device prior table, host part) over a full theta row: the kernel's priors followed,
+        with input warping, by the warp priors -- warp_priors[0] on every log a_k, warp_priors[1]
+        on every log b_k, default Normal(0, 0.3) (bask/bayesgpr.py:351-372, 462-466)."""
+        table, host_fn = as_device_priors(priors, n_kernel)
+        if not self.warp_inputs:
+            return table, host_fn
+        d_in = self._X_train.shape[1]
+        if warp_priors is None:
+            from .priors import NormalPrior
+            warp_priors = (NormalPrior(0.0, 0.3), NormalPrior(0.0, 0.3))
+        if callable(warp_priors) and not isinstance(warp_priors, (list, tuple)):
+            wtable = [(_lib.PRIOR_NONE, ())] * (2 * d_in)
+            wfn = lambda w, f=warp_priors: float(sum(f(w[k], w[d_in + k]) for k in range(d_in)))  # noqa: E731
+        else:
+            wtable, wfn = as_device_priors([warp_priors[0]] * d_in + [warp_priors[1]] * d_in, 2 * d_in)
+        if host_fn is not None or wfn is not None:
+            kf, wf = host_fn, wfn
+            host_fn = lambda th: (kf(th[:n_kernel]) if kf else 0.0) + (wf(th[n_kernel:]) if wf else 0.0)  # noqa: E731
+        return table + wtable, host_fn
+
     def _log_prob_fn(self, x, priors, warp_priors=None):
-        """Log posterior of one theta (or a (B, p) batch) -- bask/bayesgpr.py:351-379."""
+        """Log posterior of one theta (or a (B, p) batch) -- bask/bayesgpr.py:351-379.  With input
+        warping the rows are ``kernel theta ++ log a ++ log b``."""
         x = np.asarray(x, dtype=np.float64)
         single = x.ndim == 1
         X = np.atleast_2d(x)
-        table, host_fn = as_device_priors(priors, X.shape[1])
+        n_kernel = X.shape[1] - (2 * self._X_train.shape[1] if self.warp_inputs else 0)
+        table, host_fn = self._prior_table(priors, warp_priors, n_kernel)
         e = self._eng()
         e.set_priors(table)
         self._prior_key = None
@@ -330,10 +353,6 @@ class BayesGPR:
                 "Pass X and y, or ensure that you call fit before sample.")
         if priors is None:
             priors = guess_priors(self.kernel_)
-        if warp_priors is None:
-            # Normal(0, 0.3) on log a and log b of every dimension (bask/bayesgpr.py:462-466)
-            from .priors import NormalPrior
-            warp_priors = (NormalPrior(0.0, 0.3), NormalPrior(0.0, 0.3))
         data_changed = False
         if X is not None:
             y = np.asarray(y, dtype=np.float64)
@@ -393,19 +412,7 @@ class BayesGPR:
                              "are linearly independent for the best performance")
 
         e = self._eng()
-        table, host_fn = as_device_priors(priors, n_kernel)
-        if self.warp_inputs:
-            # log a_1..a_d then log b_1..b_d follow the kernel's theta (bask/bayesgpr.py:351-365)
-            d_in = added_dims // 2
-            if callable(warp_priors) and not isinstance(warp_priors, (list, tuple)):
-                wtable, wfn = [(_lib.PRIOR_NONE, ())] * added_dims, \
-                    (lambda w, f=warp_priors: float(sum(f(w[k], w[d_in + k]) for k in range(d_in))))
-            else:
-                wtable, wfn = as_device_priors([warp_priors[0]] * d_in + [warp_priors[1]] * d_in, added_dims)
-            table = table + wtable
-            if host_fn is not None or wfn is not None:
-                kf, wf = host_fn, wfn
-                host_fn = lambda th: (kf(th[:n_kernel]) if kf else 0.0) + (wf(th[n_kernel:]) if wf else 0.0)  # noqa: E731
+        table, host_fn = self._prior_table(priors, warp_priors, n_kernel)
         e.set_priors(table)
         if host_fn is None and process_group is not None and \
                 __import__("torch").distributed.get_world_size(process_group) > 1:

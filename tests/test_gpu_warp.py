@@ -81,6 +81,8 @@ def test_estimator_surface_with_warp(g6):
     np.testing.assert_allclose(mu, g6["mu_median"], rtol=RTOL, atol=1e-10)
     np.testing.assert_allclose(std, g6["std_median"], rtol=1e-5, atol=1e-9)
     np.testing.assert_allclose(gp.log_marginal_likelihood(gp.theta), g6["lml_at_median"][0], rtol=RTOL)
+    lp = gp._log_prob_fn(g6["thetas"], bask_b200.guess_priors(gp.kernel_), None)
+    np.testing.assert_allclose(lp, g6["logprob"], rtol=RTOL)
     with pytest.raises(ValueError):
         gp.predict(np.array([[0.5, 1.5]]))
     # swept acquisitions: same theta picks (random_state) and the same global-RNG Gumbel draws
