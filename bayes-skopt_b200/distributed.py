@@ -166,9 +166,25 @@ class ShardedSweep:
                 kw["ref"] = best.contiguous()
             if kind == _lib.ACQ_MES:
                 if fit is None:
+                    # the Gumbel fit needs the moments of ALL candidates, but only per theta: every
+                    # rank fits its share of the thetas (same kernel, same data -> the same bits
+                    # as a fit on one GPU) and the 5 fit parameters per theta are gathered, so the
+                    # fit cost per rank does not grow with the number of ranks
                     mu_all = self._allgather_cols(mu, sizes)
                     sd_all = self._allgather_cols(sd, sizes)
-                    fit = self.b.mes_fit(mu_all.contiguous(), sd_all.contiguous())
+                    S_all = mu_all.shape[0]
+                    s_lo, s_hi = shard_bounds(S_all, self.world, self.rank)
+                    rows = [shard_bounds(S_all, self.world, r)[1] - shard_bounds(S_all, self.world, r)[0]
+                            for r in range(self.world)]
+                    rmax = max(rows)
+                    mine = torch.zeros(rmax, 5, dtype=mu_all.dtype, device=mu_all.device)
+                    if s_hi > s_lo:
+                        mine[: s_hi - s_lo] = self.b.mes_fit(mu_all[s_lo:s_hi].contiguous(),
+                                                             sd_all[s_lo:s_hi].contiguous())
+                    parts = [torch.empty_like(mine) for _ in range(self.world)]
+                    with self.b.stream_ctx():
+                        dist.all_gather(parts, mine, group=self.group)
+                    fit = torch.cat([p_[:n_] for p_, n_ in zip(parts, rows)], dim=0).contiguous()
                 kw["fit"] = fit
                 kw["gumbel"] = gumbels[j]
             vals, skipped = self.b.per_theta(kind, mu, sd, p0, **kw)
