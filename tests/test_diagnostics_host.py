@@ -65,3 +65,34 @@ def test_sb_sequence_matches_reference():
         np.testing.assert_allclose(pts, ref_sb(6, 2, random_state=3, restarts=5), rtol=1e-9, atol=1e-12)
         np.testing.assert_allclose(more, ref_sb(8, 2, existing_points=pts, random_state=4, restarts=5),
                                    rtol=1e-9, atol=1e-12)
+
+
+def test_prior_table_with_input_warping():
+    """Host logic of warp_inputs=True: the device prior table covers kernel theta ++ log a ++ log b
+    (bask/bayesgpr.py:351-372); untyped callables end up in the host part with the right slices."""
+    import bask_b200
+    from bask_b200 import _lib
+    from bask_b200.priors import NormalPrior
+    from sklearn.gaussian_process.kernels import WhiteKernel
+    gp = bask_b200.BayesGPR(kernel=bask_b200.construct_default_kernel([0, 1]), warp_inputs=True)
+    gp._X_train = np.zeros((5, 2))
+    k = bask_b200.construct_default_kernel([0, 1]) + WhiteKernel()
+    table, host = gp._prior_table(bask_b200.guess_priors(k), None, 4)
+    assert len(table) == 4 + 4 and host is None
+    assert all(kind == _lib.PRIOR_NORMAL and tuple(par)[:2] == (0.0, 0.3) for kind, par in table[4:])
+    # a joint callable warp prior f(a_log, b_log) is summed over the dimensions on the host
+    table, host = gp._prior_table(bask_b200.guess_priors(k), lambda a, b: -(a * a + b * b), 4)
+    assert all(kind == _lib.PRIOR_NONE for kind, _ in table[4:])
+    th = np.array([0.0, 0.1, 0.2, 0.3, 1.0, 2.0, 3.0, 4.0])     # a = (1, 2), b = (3, 4)
+    np.testing.assert_allclose(host(th), -(1 + 9) - (4 + 16))
+    # typed per-parameter pair
+    table, host = gp._prior_table(bask_b200.guess_priors(k), (NormalPrior(0.0, 1.0), NormalPrior(1.0, 2.0)), 4)
+    assert host is None and [tuple(p)[:2] for _, p in table[4:]] == [(0.0, 1.0)] * 2 + [(1.0, 2.0)] * 2
+    # identity warp before any warpers exist; full theta rows get zeros appended
+    gp.kernel_ = k
+    assert gp._theta_for_device().shape == (4 + 4,) and np.all(gp._theta_for_device()[4:] == 0.0)
+    np.testing.assert_array_equal(gp.warp(np.full((3, 2), 0.25)), np.full((3, 2), 0.25))
+    gp.create_warpers(np.log([2.0, 1.0]), np.log([1.0, 1.0]))
+    np.testing.assert_allclose(gp.warp(np.full((3, 2), 0.5))[:, 0], 0.25)          # Beta(2,1).cdf(x) = x^2
+    np.testing.assert_allclose(gp.unwarp(gp.warp(np.full((3, 2), 0.3))), 0.3, rtol=1e-12)
+    np.testing.assert_allclose(gp._theta_for_device()[4:], np.log([2.0, 1.0, 1.0, 1.0]))
