@@ -1,9 +1,11 @@
-// K1+K2: batched-theta Gram build + FP64 Cholesky + forward solve + LML + log-prior,
-// one CTA per theta.  Left-looking blocked factorisation, 32-column panels:
+// K2: batched-theta FP64 Cholesky + forward solve + LML + log-prior, one CTA (or a cluster of
+// 2-8 CTAs when the batch leaves SMs idle) per theta.  Left-looking blocked factorisation,
+// 32-column panels:
 //   * the Gram matrix arrives in the L2-resident factor slab, written by the K1 kernel of the
 //     same stream (bgp_gram.cu) in exactly the tiled layout consumed here;
 //   * trailing updates and the panel triangular solve are DMMA.8x8x4 GEMMs whose A operand
-//     streams from the slab in 16-byte loads, B operand is staged in shared memory;
+//     streams from the slab through a per-warp cp.async ring, B operand is staged in shared
+//     memory;
 //   * y rides along as one extra row, so z = L^-1 y (and y^T K^-1 y = |z|^2) falls out of the
 //     same panel solves; in factorise mode identity rows ride along too and come out as
 //     L^-T, which the candidate sweep consumes.
@@ -541,7 +543,7 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
       BGP_STAMP(4);
 
       // ------------------------------------------------ phase 2: rows below the block, 8-row
-      // tiles dealt evenly to the warps (up to four per warp and round)
+      // tiles dealt evenly to the warps (at most MAXT per warp and round)
       // 32-row groups below the diagonal and identity-row groups; with CS == 2 groups alternate
       // between the two CTAs of the cluster and the y tile belongs to rank 0
       // tiles of this panel: the y tile, the 4 (P-1-k) tiles below the block, the identity-row
@@ -551,7 +553,7 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
       // (rounded up, so that the y tile -- whose |z|^2 the epilogue of rank 0 sums -- stays on rank 0)
       const int tlo = (Tg * crank + CS - 1) / CS, T = (Tg * (crank + 1) + CS - 1) / CS - tlo;
       // warp w owns the contiguous tiles [w0, w0 + mine); every warp runs the same number of
-      // rounds (barriers inside when K is chunked), each with at most four of its tiles
+      // rounds (barriers inside when K is chunked), each with at most MAXT of its tiles
       // worker warps (warp 0 is busy when overlapping).  The deal starts with the warps that have
       // an SM sub-partition to themselves and ends with warp NW/2, which shares its FP64 pipe with
       // the potrf warp: with few tiles left the K-loops run alone on their pipes and the
