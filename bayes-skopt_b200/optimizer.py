@@ -226,63 +226,60 @@ class Optimizer:
             self._expected_optimum_cache = (key, x)
         return x
 
+    def _optimality_margins(self, n_space_samples, n_gp_samples, n_random_starts, use_mean_gp, normalized_scores,
+                            random_state):
+        """Per joint posterior draw: by how much the best of ``n_space_samples`` random points beats the
+        expected optimum (row 0 of the draw), optionally in units of the draw's standard deviation."""
+        pts = [self._expected_optimum(n_random_starts, random_state)]
+        pts += self.space.rvs(n_samples=n_space_samples, random_state=random_state)
+        draws = self.gp.sample_y(self.space.transform(pts), n_samples=n_gp_samples, sample_mean=use_mean_gp,
+                                 random_state=random_state)                       # (1 + n_space, n_gp)
+        gain = draws[0][None, :] - draws                                           # > 0: the point is better
+        if normalized_scores:
+            gain = gain / np.std(draws, axis=0)
+        return gain.max(axis=0)
+
     def probability_of_optimality(self, threshold, n_space_samples=500, n_gp_samples=200, n_random_starts=100,
                                   use_mean_gp=True, normalized_scores=True, random_state=None):
         """Probability that the current expected optimum cannot be improved by more than
-        ``threshold`` (float or list), from joint posterior draws over the optimum and
-        ``n_space_samples`` random points (bask/optimizer.py:447-525).  The draws come from the
-        device ``sample_y`` (Cholesky instead of numpy's SVD: same distribution, other variates)."""
-        X_orig = [self._expected_optimum(n_random_starts, random_state)]
-        X_orig.extend(self.space.rvs(n_samples=n_space_samples, random_state=random_state))
-        X_trans = self.space.transform(X_orig)
-        score_samples = self.gp.sample_y(X_trans, n_samples=n_gp_samples, sample_mean=use_mean_gp,
-                                         random_state=random_state)
-        if normalized_scores:
-            std = np.std(score_samples, axis=0)
-        if not is_listlike(threshold):
-            threshold = [threshold]
-        probabilities = []
-        for eps in threshold:
-            if normalized_scores:
-                diff = (score_samples[0][None, :] - score_samples) / std
-            else:
-                diff = score_samples[0][None, :] - score_samples
-            probabilities.append(((diff - eps).max(axis=0) < 0.0).mean())
-        if len(probabilities) == 1:
-            return probabilities[0]
-        return probabilities
+        ``threshold`` (a float, or a list -> list of probabilities): the share of joint posterior
+        draws in which no random point beats it by that margin (bask/optimizer.py:447-525).  The
+        draws come from the device ``sample_y`` (Cholesky instead of numpy's SVD: same
+        distribution, other variates)."""
+        best_gain = self._optimality_margins(n_space_samples, n_gp_samples, n_random_starts, use_mean_gp,
+                                             normalized_scores, random_state)
+        many = is_listlike(threshold)
+        probs = [float(np.mean(best_gain - eps < 0.0)) for eps in (threshold if many else [threshold])]
+        return probs if many and len(probs) != 1 else probs[0]
 
     def expected_optimality_gap(self, max_tries=3, n_probabilities=50, n_space_samples=500, n_gp_samples=200,
                                 n_random_starts=100, tol=0.01, use_mean_gp=True, normalized_scores=True,
                                 random_state=None):
         """Expected optimality gap of the current optimum w.r.t. sampled consistent optima
-        (bask/optimizer.py:527-620)."""
+        (bask/optimizer.py:527-620): the threshold beyond which the optimum is almost surely
+        optimal is located with a bounded scalar search, then the gap distribution on
+        ``n_probabilities`` thresholds below it is integrated."""
         from scipy.optimize import minimize_scalar
-        random_state = check_random_state(random_state)
-        seed = random_state.randint(0, 2 ** 32 - 1, dtype=np.int64)
-        kw = dict(n_random_starts=n_random_starts, n_gp_samples=n_gp_samples, n_space_samples=n_space_samples,
-                  use_mean_gp=use_mean_gp, normalized_scores=normalized_scores, random_state=seed)
+        seed = check_random_state(random_state).randint(0, 2 ** 32 - 1, dtype=np.int64)
+        common = dict(n_random_starts=n_random_starts, n_gp_samples=n_gp_samples, n_space_samples=n_space_samples,
+                      use_mean_gp=use_mean_gp, normalized_scores=normalized_scores, random_state=seed)
 
-        def func(threshold):
-            prob = self.probability_of_optimality(threshold=threshold, **kw)
-            return (prob - 1.0) ** 2 + threshold ** 2 * 1e-3
+        def objective(eps):
+            return (self.probability_of_optimality(threshold=eps, **common) - 1.0) ** 2 + 1e-3 * eps ** 2
 
-        max_observed_gap = np.max(self.yi) - np.min(self.yi)
+        span = np.max(self.yi) - np.min(self.yi)
+        upper = None
         for _ in range(max_tries):
             try:
-                upper_threshold = minimize_scalar(func, bounds=(0.0, max_observed_gap), tol=tol).x
+                upper = minimize_scalar(objective, bounds=(0.0, span), method="bounded", options={"xatol": tol}).x
                 break
             except ValueError:
-                pass
-        else:
+                continue
+        if upper is None:
             raise ValueError("Determining the upper threshold was not possible.")
-        thresholds = list(np.linspace(0, upper_threshold, num=n_probabilities))
-        probabilities = self.probability_of_optimality(thresholds, **kw)
-        expected_gap = 0.0
-        for i in range(0, len(probabilities) - 1):
-            p = probabilities[i + 1] - probabilities[i]
-            expected_gap += p * thresholds[i + 1]
-        return expected_gap
+        grid = np.linspace(0, upper, num=n_probabilities)
+        cdf = np.asarray(self.probability_of_optimality(list(grid), **common), dtype=np.float64).reshape(-1)
+        return float(np.sum(np.diff(cdf) * grid[1:]))
 
     def optimum_intervals(self, hdi_prob=0.95, multimodal=True, opt_samples=200, space_samples=500,
                           only_mean=True, random_state=None):

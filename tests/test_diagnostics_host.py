@@ -96,3 +96,42 @@ def test_prior_table_with_input_warping():
     np.testing.assert_allclose(gp.warp(np.full((3, 2), 0.5))[:, 0], 0.25)          # Beta(2,1).cdf(x) = x^2
     np.testing.assert_allclose(gp.unwarp(gp.warp(np.full((3, 2), 0.3))), 0.3, rtol=1e-12)
     np.testing.assert_allclose(gp._theta_for_device()[4:], np.log([2.0, 1.0, 1.0, 1.0]))
+
+
+def test_diagnostics_arithmetic_with_a_stub_gp():
+    """The optimiser diagnostics on a stub GP whose joint draws are known: the probabilities and the
+    gap must equal a direct re-computation from the same draws (bask/optimizer.py:505-525, 610-620)."""
+    import bask_b200
+
+    class StubGP:
+        warp_inputs = False
+        chain_ = None
+        kernel_ = True
+
+        def predict(self, X):
+            return np.array([np.sum((np.asarray(X) - 0.4) ** 2)])
+
+        def sample_y(self, X, n_samples=1, sample_mean=True, random_state=None):
+            rs = np.random.RandomState(1234)
+            base = np.sum((np.asarray(X) - 0.4) ** 2, axis=1)
+            return base[:, None] + 0.05 * rs.randn(len(X), n_samples)
+
+    opt = bask_b200.Optimizer([(0.0, 1.0), (0.0, 1.0)], n_initial_points=0, random_state=0)
+    opt.gp = StubGP()
+    opt.Xi = [[0.1, 0.2], [0.5, 0.4], [0.9, 0.9]]
+    opt.yi = [0.13, 0.01, 0.5]
+    kw = dict(n_space_samples=60, n_gp_samples=40, n_random_starts=2, random_state=7)
+    ps = opt.probability_of_optimality([0.0, 0.5, 1.0, 3.0], **kw)
+    # direct re-computation
+    x0 = opt._expected_optimum(2, 7)
+    pts = [x0] + opt.space.rvs(n_samples=60, random_state=7)
+    draws = StubGP().sample_y(opt.space.transform(pts), n_samples=40)
+    std = np.std(draws, axis=0)
+    want = [float((((draws[0][None, :] - draws) / std - eps).max(axis=0) < 0.0).mean()) for eps in (0.0, 0.5, 1.0, 3.0)]
+    np.testing.assert_allclose(ps, want)
+    assert ps == sorted(ps) and opt.probability_of_optimality(3.0, **kw) == ps[-1]
+    raw = opt.probability_of_optimality(0.02, normalized_scores=False, **kw)
+    assert raw == float(((draws[0][None, :] - draws - 0.02).max(axis=0) < 0.0).mean())
+    gap = opt.expected_optimality_gap(n_probabilities=15, n_space_samples=60, n_gp_samples=40, n_random_starts=2,
+                                      random_state=3)
+    assert np.isfinite(gap) and 0.0 <= gap <= max(opt.yi) - min(opt.yi)
