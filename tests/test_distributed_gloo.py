@@ -87,7 +87,7 @@ class OracleBackend:
         return (torch.nan_to_num(vals, nan=0.0, posinf=0.0, neginf=0.0) * keep).sum(dim=0) / vals.shape[0]
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, n_theta=3):
     sys.path.insert(0, REPO)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -98,9 +98,9 @@ def _worker(rank, world, port, q):
     g = dict(np.load(os.path.join(REPO, "tests", "golden", "g1_branin_n20.npz")))
     be = OracleBackend(g, 2)
     X = g["Xc"][:203]          # ragged split: 102 + 101
-    thetas = g["thetas"][:3]
+    thetas = g["thetas"][:n_theta]
     with np.errstate(all="ignore"):
-        gum = -np.log(-np.log(g["mes_uniforms"][:3]))
+        gum = -np.log(-np.log(g["mes_uniforms"][:n_theta]))
     acqs = [(_lib.ACQ_EI, float("nan")), (_lib.ACQ_TTEI, float("nan")), (_lib.ACQ_LCB, 1.96),
             (_lib.ACQ_MEAN, 0.0), (_lib.ACQ_MES, float("nan"))]
     out = ShardedSweep(be, None).evaluate(X, thetas, acqs, {4: gum})
@@ -141,6 +141,35 @@ def test_sharded_sweep_equals_single_process():
     for j, name in enumerate(["ei", "ttei", "lcb", "mean", "mes"]):
         np.testing.assert_allclose(res[0][1][j], expect[j], rtol=1e-9, atol=1e-300, err_msg=name)
         assert np.argmax(res[0][1][j]) == np.argmax(expect[j])
+
+
+def test_sharded_sweep_more_ranks_than_thetas():
+    """World 3, two thetas: one rank owns no theta of the theta-sharded MES fit and the candidate
+    blocks are ragged (68 + 68 + 67); every rank must still return the single-process answer."""
+    sys.path.insert(0, REPO)
+    from oracle import acq_oracle as A
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 3, port, q, 2)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[2] for r in res] == [(0, 68), (68, 136), (136, 203)]
+    np.testing.assert_array_equal(res[0][1], res[1][1])
+    np.testing.assert_array_equal(res[0][1], res[2][1])
+    g = dict(np.load(os.path.join(REPO, "tests", "golden", "g1_branin_n20.npz")))
+    be = OracleBackend(g, 2)
+    mu, sd = be.moments(g["thetas"][:2], g["Xc"][:203])
+    mu, sd = mu.numpy(), sd.numpy()
+    with np.errstate(all="ignore"):
+        mes = np.mean([A.max_value_search(mu[s], sd[s], uniforms=g["mes_uniforms"][s]) for s in range(2)], axis=0)
+        ei = np.mean([A.expected_improvement(mu[s], sd[s]) for s in range(2)], axis=0)
+    np.testing.assert_allclose(res[0][1][4], mes, rtol=1e-9, atol=1e-300)
+    np.testing.assert_allclose(res[0][1][0], ei, rtol=1e-9, atol=1e-300)
 
 
 def test_shard_bounds_cover_everything():
