@@ -125,6 +125,7 @@ class Engine:
     def __del__(self):
         try:
             if getattr(self, "h", None):
+                self.close_peers()
                 self.lib.bgp_destroy(self.h)
                 self.h = None
         except Exception:
@@ -289,6 +290,60 @@ class Engine:
         check(self.lib.bgp_argmax(self.h, _ptr(v), v.shape[0], _ptr(idx), self._st), "bgp_argmax")
         self.launches += 1
         return idx
+
+    # ------------------------------------------------------------------ multi-GPU plumbing
+    def connect_peers(self, group, max_walkers):
+        """Maps the walker-exchange blocks of all ranks of `group` into this process (cudaIpc over NVLink
+        P2P): after this the sharded MCMC needs neither NCCL nor the host between propose and accept.
+        torch.distributed only carries the 64-byte handles here."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        peers = getattr(self, "_peers", None)
+        if peers is not None and peers == (id(group), world, rank) and max_walkers <= self._peer_cap:
+            return
+        self.close_peers()
+        cap = max(int(max_walkers), 256)
+        mine = (C.c_ubyte * _lib.IPC_HANDLE_BYTES)()
+        check(self.lib.bgp_peer_export(self.h, cap, mine), "bgp_peer_export")
+        with torch.cuda.stream(self.stream):
+            t = torch.tensor(list(mine), dtype=torch.uint8, device=self.device)
+            allh = torch.empty(world * _lib.IPC_HANDLE_BYTES, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(allh, t, group=group)
+        self.stream.synchronize()
+        raw = bytes(allh.cpu().numpy().tobytes())
+        check(self.lib.bgp_peer_connect(self.h, raw, rank, world), "bgp_peer_connect")
+        dist.barrier(group=group)           # every rank has mapped every block before anyone stores into one
+        self._peers, self._peer_cap, self._peer_group = (id(group), world, rank), cap, group
+        self._mc_buffers_sharded = None
+
+    def close_peers(self):
+        if getattr(self, "_peers", None) is not None:
+            self.stream.synchronize()
+            self.lib.bgp_peer_close(self.h)
+            self._peers = None
+
+    def mcmc_sharded(self, pos, n_steps, seed, group, a=2.0, buffers=None):
+        """Walker-sharded run over the ranks of `group` (one CUDA graph per rank, peer stores for the
+        log-prob exchange).  Same buffers as ``mcmc``; the chain is identical on every rank."""
+        W, p = pos.shape
+        self.connect_peers(group, W)
+        if buffers is None or buffers["chain"].shape != (n_steps, W, p):
+            buffers = dict(pos=self.empty(W, p), lp=self.empty(W), chain=self.empty(n_steps, W, p),
+                           lpc=self.empty(n_steps, W), acc=self.empty(W, dtype=torch.int32))
+        src = pos if torch.is_tensor(pos) else self.to_dev(pos)
+        with torch.cuda.stream(self.stream):
+            buffers["pos"].copy_(src, non_blocking=True)
+        check(self.lib.bgp_mcmc_run_sharded(self.h, _ptr(buffers["pos"]), _ptr(buffers["lp"]), W, n_steps, float(a),
+                                            C.c_uint64(int(seed) & (2 ** 64 - 1)), _ptr(buffers["chain"]),
+                                            _ptr(buffers["lpc"]), _ptr(buffers["acc"]), self._st),
+              "bgp_mcmc_run_sharded")
+        self.launches += 4 + 11 * n_steps
+        return buffers
+
+    def peer_timed_out(self):
+        flag = C.c_int(0)
+        check(self.lib.bgp_peer_status(self.h, C.byref(flag)), "bgp_peer_status")
+        return bool(flag.value)
 
     # ------------------------------------------------------------------ K3
     def mcmc(self, pos, n_steps, seed, a=2.0, buffers=None):

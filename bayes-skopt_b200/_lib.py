@@ -61,7 +61,13 @@ _SIGNATURES = {
     "bgp_pvrs_combine": [_P, _P, _P, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P],
     "bgp_vr_combine": [_P, _P, C.c_int, C.c_int64, _P, _P, _P, _P, _P],
     "bgp_slab_trmm": [_P, _P, C.c_int, _P, C.c_int, _P, _P, _P],
+    "bgp_peer_export": [_P, C.c_int, _P],
+    "bgp_peer_connect": [_P, _P, C.c_int, C.c_int],
+    "bgp_peer_close": [_P],
+    "bgp_peer_status": [_P, C.POINTER(C.c_int)],
+    "bgp_mcmc_run_sharded": [_P, _P, _P, C.c_int, C.c_int, C.c_double, C.c_uint64, _P, _P, _P, _P],
 }
+IPC_HANDLE_BYTES = 64
 EXPORTED = tuple(_SIGNATURES) + ("bgp_last_error",)
 
 _lib = None

@@ -10,7 +10,8 @@ What runs where
     geometric median of the chain.
 
 Deliberate differences from the reference, all additive or documented:
-  * ``warp_inputs=True`` is not implemented yet (SURVEY.md section 8f row N1) and raises;
+  * ``warp_inputs=True`` warps every point set per theta row on the device (Beta-CDF device
+    function); the host keeps the reference's ``warp``/``unwarp``/``create_warpers`` surface;
   * the MCMC random stream is Philox on device, so chains agree with emcee in distribution,
     not draw by draw (BASELINE.json north_star);
   * ``sample``/``fit`` take an extra ``n_walkers`` alias and ``with_hyperparam(theta)``
@@ -79,7 +80,8 @@ class BayesGPR:
         self._dense = {}             # lazily extracted / user-assigned L_, K_inv_, alpha_
         self._mc_buffers = None
         self._prior_key = None
-        self.timings_ = {}
+        self.chain_generation_ = 0   # bumped whenever chain_ is replaced (cache keys of the diagnostics)
+        self.timings_ = {}           # CUDA-event milliseconds of the last sample(): "mcmc", "factorize"
 
     # ------------------------------------------------------------------ engine plumbing
     def _eng(self):
@@ -422,9 +424,16 @@ class BayesGPR:
             chain_steps, pos_out, accepted = sharded_mcmc(e, pos, n_samples, seed, a, process_group)
             self._acceptance = accepted / max(n_samples, 1)
         elif host_fn is None:
-            buf = e.mcmc(pos, n_samples, seed, a=a, buffers=self._mc_buffers)
+            import torch
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            with torch.cuda.nvtx.range("bgp.sample.mcmc"):
+                ev[0].record(e.stream)
+                buf = e.mcmc(pos, n_samples, seed, a=a, buffers=self._mc_buffers)
+                ev[1].record(e.stream)
             self._mc_buffers = buf
             e.sync()
+            self.timings_["mcmc_ms"] = ev[0].elapsed_time(ev[1])
+            self.timings_["mcmc_logprob_evals"] = int(n_walkers * (1 + n_samples))
             chain_steps = buf["chain"].cpu().numpy()
             pos_out = buf["pos"].cpu().numpy()
             self._acceptance = buf["acc"].cpu().numpy() / max(n_samples, 1)
@@ -437,6 +446,7 @@ class BayesGPR:
             self.chain_ = np.concatenate([self.chain_, chain])
         else:
             self.chain_ = chain
+        self.chain_generation_ += 1
         # point estimate: the factorisation at the geometric median is only enqueued here; its
         # LinAlgError check and the LML read-back happen at the first use (no host round trip)
         median = geometric_median(self.chain_)
@@ -579,7 +589,14 @@ class BayesGPR:
                 white, name = find_zeroable_white(self.kernel_)
                 if white is not None:
                     self.noise_ = white.noise_level
+                    n_free = self.kernel_.n_dims
                     self.kernel_.set_params(**{name: WhiteKernel(noise_level=0.0)})
+                    if self.kernel_.n_dims != n_free:
+                        # noise=<float>: skopt's fixed White leaf has just become a free hyper-parameter
+                        # (bask samples it, starting from log(noise_)): the device program gets the new slot
+                        self._eng().set_kernel(self.kernel_,
+                                               n_warp=self._X_train.shape[1] if self.warp_inputs else 0)
+                        self._prior_key = None
         self.y_train_std_ = self._y_train_std
         self.y_train_mean_ = self._y_train_mean
 

@@ -324,6 +324,13 @@ __global__ void combine_kernel(const double* __restrict__ v, int S, int m, const
   out[i] = acc;
 }
 
+// mes_epilogue_kernel keeps the K max-value draws in dynamic shared memory
+constexpr int MES_MAX_K = 24576;
+cudaError_t prepare_acq() {
+  return cudaFuncSetAttribute(mes_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              MES_MAX_K * (int)sizeof(double));
+}
+
 size_t acq_scratch_doubles(int S, int m) {
   const size_t nblk = (m + MES_CH - 1) / MES_CH;
   return (size_t)S * (ST + MS + MES_PTS + 8 + 5 + 4) + 2 * (size_t)S * nblk * MES_PTS + (size_t)S * m + 64;
@@ -404,7 +411,7 @@ cudaError_t launch_acq_per_theta(const AcqArgs& A, cudaStream_t stream) {
       mean_lcb_kernel<<<ge, 256, 0, stream>>>(A.mu, A.sd, m, A.kind, A.p0, A.per_theta);
       break;
     case BGP_ACQ_MES: {
-      if (!A.u32 || A.K <= 0) return cudaErrorInvalidValue;
+      if (!A.u32 || A.K <= 0 || A.K > MES_MAX_K) return cudaErrorInvalidValue;
       dim3 gm((m + 127) / 128, S);
       mes_epilogue_kernel<<<gm, 128, A.K * sizeof(double), stream>>>(A.mu, A.sd, m, A.u32, A.K,
                                                                      A.mes_fit ? A.mes_fit : w.fit, A.per_theta);

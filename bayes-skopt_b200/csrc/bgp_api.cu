@@ -35,6 +35,7 @@ struct DevBuf {
 struct GraphKey {
   const void *pos, *lp, *chain, *lpc, *acc;
   int W, T, n, d, p;
+  int rank, world;   // 0, 1 for the single-GPU run
   double a;
   bool operator==(const GraphKey& o) const { return std::memcmp(this, &o, sizeof(GraphKey)) == 0; }
 };
@@ -50,8 +51,13 @@ struct bgp_handle_s {
   DevBuf slabs_scratch;      // one factor slab per resident CTA (logprob mode)
   DevBuf xt_scratch;         // scaled inputs per resident CTA when they exceed shared memory
   DevBuf acq_scratch, extract_scratch;
+  DevBuf sweep_scratch;      // windowed sweep: one k* tile per resident CTA
   DevBuf warp_x, warp_xc, warp_xt;   // per-theta warped copies of X / candidates / Thompson points
   DevBuf mc_colour, mc_movers, mc_q, mc_factors, mc_newlp, mc_seed;
+  // multi-GPU walker sharding: this rank's exchange block and the peers' blocks as mapped here
+  DevBuf xchg;
+  bgp::PeerXchg peers;
+  bool have_peers = false;
   uint64_t* seed_pinned = nullptr;
   cudaGraphExec_t graph = nullptr;
   GraphKey key;
@@ -83,6 +89,9 @@ int bgp_create(bgp_handle_t* out, int device) {
   h->device = device;
   h->sms = prop.multiProcessorCount;
   std::memset(&h->key, 0, sizeof(h->key));
+  CUDA_TRY(bgp::prepare_mcmc());
+  CUDA_TRY(bgp::prepare_acq());
+  CUDA_TRY(bgp::prepare_sweep());
   CUDA_TRY(cudaMallocHost((void**)&h->seed_pinned, sizeof(uint64_t)));
   CUDA_TRY(h->mc_seed.ensure(sizeof(uint64_t)));
   *out = h;
@@ -93,8 +102,10 @@ int bgp_destroy(bgp_handle_t h) {
   CHECK_H(h);
   cudaSetDevice(h->device);
   if (h->graph) cudaGraphExecDestroy(h->graph);
+  bgp_peer_close(h);
+  h->xchg.release();
   for (DevBuf* b : {&h->prog, &h->fixed_ls, &h->priors, &h->X, &h->y, &h->alpha, &h->slabs_scratch, &h->xt_scratch,
-                    &h->acq_scratch, &h->extract_scratch, &h->warp_x, &h->warp_xc, &h->warp_xt, &h->mc_colour, &h->mc_movers, &h->mc_q,
+                    &h->acq_scratch, &h->extract_scratch, &h->sweep_scratch, &h->warp_x, &h->warp_xc, &h->warp_xt, &h->mc_colour, &h->mc_movers, &h->mc_q,
                     &h->mc_factors, &h->mc_newlp, &h->mc_seed})
     b->release();
   if (h->seed_pinned) cudaFreeHost(h->seed_pinned);
@@ -350,7 +361,13 @@ int bgp_predict_batched(bgp_handle_t h, const double* theta_dev, int S, const do
   A.prog = h->prog.as<DevProgram>(); A.fixed_ls = h->fixed_ls.as<double>();
   A.y_mean = y_mean; A.y_std = y_std; A.n = h->n; A.d = h->d; A.S = S; A.m = m; A.R = R;
   A.noise_off = noise_off;
-  cudaError_t e = bgp::launch_sweep(A, (cudaStream_t)stream);
+  A.n_leaves = h->host_prog.n_leaves; A.ks_scratch = nullptr; A.ks_scratch_stride = 0;
+  if (bgp::sweep_is_windowed(h->n, h->d, R, h->host_prog.n_leaves)) {
+    const size_t per_cta = bgp::sweep_scratch_doubles(h->n);
+    CUDA_TRY(h->sweep_scratch.ensure(sizeof(double) * per_cta * (size_t)h->sms));
+    A.ks_scratch = h->sweep_scratch.as<double>(); A.ks_scratch_stride = (long long)per_cta;
+  }
+  cudaError_t e = bgp::launch_sweep(A, h->sms, (cudaStream_t)stream);
   if (e != cudaSuccess) return fail("sweep launch (n too large for the shared-memory resident tile?)", e);
   return 0;
 }
@@ -461,13 +478,12 @@ int bgp_dense_cholesky(bgp_handle_t h, const double* a_dev, int m, int64_t lda, 
   CHECK_H(h);
   if (!a_dev || m <= 0 || lda < m || !slab_dev || !info_dev) return fail("bad dense-cholesky arguments");
   CUDA_TRY(cudaSetDevice(h->device));
-  CUDA_TRY(bgp::prepare_chol(m));
+  if (bgp::prepare_chol(m) != cudaSuccess) return fail("m too large for the shared-memory plan of the factorisation kernel");
   bgp::CholArgs A;
   std::memset(&A, 0, sizeof(A));
   A.slabs = slab_dev; A.info = info_dev; A.n = m; A.d = 1; A.batch = 1; A.aug = 0; A.slab_per_block = 0;
   A.dense = a_dev; A.ldd = lda; A.jitter = jitter;
   CUDA_TRY(bgp::launch_chol(A, 1, h->sms, (cudaStream_t)stream));
-  if (h->have_data) CUDA_TRY(bgp::prepare_chol(h->n));
   return 0;
 }
 
@@ -553,12 +569,30 @@ int bgp_mcmc_seed_source(bgp_handle_t h, const uint64_t* seed_dev) {
   return 0;
 }
 
+// slice [lo, hi) of `count` items owned by `rank` (the first count % world ranks get one extra)
+static void shard(int count, int world, int rank, int* lo, int* cnt) {
+  const int q = count / world, r = count % world;
+  *lo = rank * q + (rank < r ? rank : r);
+  *cnt = q + (rank < r ? 1 : 0);
+}
+
+// sharded = every rank evaluates its slice of the proposals and the accept kernel starts with the peer
+// exchange (bgp_mcmc.cu); the chain is identical on every rank and identical to the single-GPU one
 static int mcmc_enqueue(bgp_handle_t h, double* pos, double* lp, int W, int T, double a, double* chain,
-                        double* lpc, int32_t* acc, cudaStream_t st) {
+                        double* lpc, int32_t* acc, bool sharded, cudaStream_t st) {
   const int p = h->host_prog.n_theta;
   const uint64_t* sp = h->mc_seed.as<uint64_t>();
+  const int world = sharded ? h->peers.world : 1, rank = sharded ? h->peers.rank : 0;
+  int lo = 0, cnt = W;
   if (acc) CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(int32_t) * W, st));
-  if (logprob_impl(h, pos, W, nullptr, lp, nullptr, nullptr, st)) return -1;
+  if (sharded) {
+    shard(W, world, rank, &lo, &cnt);
+    if (cnt > 0 && logprob_impl(h, pos + (size_t)lo * p, cnt, nullptr, h->mc_newlp.as<double>(), nullptr, nullptr, st))
+      return -1;
+    CUDA_TRY(bgp::launch_xchg_gather(h->peers, h->mc_newlp.as<double>(), lo, cnt, W, lp, st));
+  } else if (logprob_impl(h, pos, W, nullptr, lp, nullptr, nullptr, st)) {
+    return -1;
+  }
   for (int t = 0; t < T; ++t) {
     CUDA_TRY(bgp::launch_split(W, 0, sp, t, h->mc_colour.as<int32_t>(), st));
     for (int half = 0; half < 2; ++half) {
@@ -566,20 +600,118 @@ static int mcmc_enqueue(bgp_handle_t h, double* pos, double* lp, int W, int T, d
       CUDA_TRY(bgp::launch_propose(pos, h->mc_colour.as<int32_t>(), W, p, half, a, 0, sp, t,
                                    h->mc_q.as<double>(), h->mc_factors.as<double>(),
                                    h->mc_movers.as<int32_t>(), st));
-      if (logprob_impl(h, h->mc_q.as<double>(), ns, nullptr, h->mc_newlp.as<double>(), nullptr, nullptr, st))
-        return -1;
-      CUDA_TRY(bgp::launch_accept(pos, lp, h->mc_q.as<double>(), h->mc_factors.as<double>(),
-                                  h->mc_newlp.as<double>(), h->mc_movers.as<int32_t>(), W, p, half, 0, sp, t,
-                                  acc, (half == 1 && chain) ? chain + (size_t)t * W * p : nullptr,
-                                  (half == 1 && lpc) ? lpc + (size_t)t * W : nullptr, st));
+      double* chain_t = (half == 1 && chain) ? chain + (size_t)t * W * p : nullptr;
+      double* lpc_t = (half == 1 && lpc) ? lpc + (size_t)t * W : nullptr;
+      if (sharded) {
+        shard(ns, world, rank, &lo, &cnt);
+        if (cnt > 0 && logprob_impl(h, h->mc_q.as<double>() + (size_t)lo * p, cnt, nullptr, h->mc_newlp.as<double>(),
+                                    nullptr, nullptr, st))
+          return -1;
+        CUDA_TRY(bgp::launch_accept_xchg(h->peers, pos, lp, h->mc_q.as<double>(), h->mc_factors.as<double>(),
+                                         h->mc_newlp.as<double>(), lo, cnt, h->mc_movers.as<int32_t>(), W, p, half,
+                                         0, sp, t, acc, chain_t, lpc_t, st));
+      } else {
+        if (logprob_impl(h, h->mc_q.as<double>(), ns, nullptr, h->mc_newlp.as<double>(), nullptr, nullptr, st))
+          return -1;
+        CUDA_TRY(bgp::launch_accept(pos, lp, h->mc_q.as<double>(), h->mc_factors.as<double>(),
+                                    h->mc_newlp.as<double>(), h->mc_movers.as<int32_t>(), W, p, half, 0, sp, t,
+                                    acc, chain_t, lpc_t, st));
+      }
     }
   }
   return 0;
 }
 
+static int mcmc_run_impl(bgp_handle_t h, double* pos_dev, double* lp_dev, int W, int T, double a, uint64_t seed,
+                         double* chain_dev, double* lp_chain_dev, int32_t* accepted_dev, bool sharded, void* stream);
+
 int bgp_mcmc_run(bgp_handle_t h, double* pos_dev, double* lp_dev, int W, int T, double a, uint64_t seed,
                  double* chain_dev, double* lp_chain_dev, int32_t* accepted_dev, void* stream) {
   CHECK_H(h);
+  return mcmc_run_impl(h, pos_dev, lp_dev, W, T, a, seed, chain_dev, lp_chain_dev, accepted_dev, false, stream);
+}
+
+int bgp_mcmc_run_sharded(bgp_handle_t h, double* pos_dev, double* lp_dev, int W, int T, double a, uint64_t seed,
+                         double* chain_dev, double* lp_chain_dev, int32_t* accepted_dev, void* stream) {
+  CHECK_H(h);
+  if (!h->have_peers) return fail("bgp_peer_connect has not been called");
+  if (W > h->peers.cap) return fail("more walkers than the exchange block was exported for");
+  if (stream == nullptr) return fail("the sharded run needs a non-default stream (it is a CUDA graph)");
+  return mcmc_run_impl(h, pos_dev, lp_dev, W, T, a, seed, chain_dev, lp_chain_dev, accepted_dev, true, stream);
+}
+
+/* ---- peer exchange blocks (cudaIpc) ---- */
+int bgp_peer_export(bgp_handle_t h, int max_walkers, void* ipc_handle_out) {
+  CHECK_H(h);
+  if (max_walkers < 2 || max_walkers > 8192 || !ipc_handle_out) return fail("bad peer-export arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (h->have_peers) return fail("peers are already connected (bgp_peer_close first)");
+  const size_t bytes = sizeof(double) * 2 * (size_t)max_walkers + sizeof(unsigned long long) * 16;
+  h->xchg.release();
+  CUDA_TRY(h->xchg.ensure(bytes));
+  CUDA_TRY(cudaMemset(h->xchg.p, 0, bytes));
+  cudaIpcMemHandle_t ih;
+  CUDA_TRY(cudaIpcGetMemHandle(&ih, h->xchg.p));
+  static_assert(sizeof(cudaIpcMemHandle_t) == BGP_IPC_HANDLE_BYTES, "IPC handle size");
+  std::memcpy(ipc_handle_out, &ih, sizeof(ih));
+  h->peers.cap = max_walkers;
+  return 0;
+}
+
+int bgp_peer_connect(bgp_handle_t h, const void* ipc_handles, int rank, int world) {
+  CHECK_H(h);
+  if (!ipc_handles || world < 1 || world > 8 || rank < 0 || rank >= world) return fail("bad peer-connect arguments");
+  if (!h->xchg.p) return fail("bgp_peer_export has not been called");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int cap = h->peers.cap;
+  std::memset(&h->peers, 0, sizeof(h->peers));
+  h->peers.cap = cap; h->peers.rank = rank; h->peers.world = world;
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { h->peers.block[r] = h->xchg.as<double>(); continue; }
+    cudaIpcMemHandle_t ih;
+    std::memcpy(&ih, static_cast<const char*>(ipc_handles) + (size_t)r * sizeof(ih), sizeof(ih));
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      for (int k = 0; k < r; ++k) if (k != rank && h->peers.block[k]) cudaIpcCloseMemHandle(h->peers.block[k]);
+      return fail("cudaIpcOpenMemHandle (no peer access between the GPUs of this box?)", e);
+    }
+    h->peers.block[r] = static_cast<double*>(ptr);
+  }
+  h->have_peers = true;
+  h->have_graph = false;
+  return 0;
+}
+
+int bgp_peer_close(bgp_handle_t h) {
+  CHECK_H(h);
+  if (!h->have_peers) return 0;
+  cudaSetDevice(h->device);
+  if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
+  h->have_graph = false;
+  for (int r = 0; r < h->peers.world; ++r)
+    if (r != h->peers.rank && h->peers.block[r]) cudaIpcCloseMemHandle(h->peers.block[r]);
+  h->have_peers = false;
+  return 0;
+}
+
+/* 1 when a peer exchange of this handle ever timed out (a rank died or never launched): the chain of that run
+ * is invalid */
+int bgp_peer_status(bgp_handle_t h, int* timed_out) {
+  CHECK_H(h);
+  if (!timed_out) return fail("null out");
+  *timed_out = 0;
+  if (!h->xchg.p) return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  unsigned long long w = 0;
+  CUDA_TRY(cudaMemcpy(&w, reinterpret_cast<const char*>(h->xchg.p) + sizeof(double) * 2 * (size_t)h->peers.cap +
+                              sizeof(unsigned long long) * 9, sizeof(w), cudaMemcpyDeviceToHost));
+  *timed_out = w != 0;
+  return 0;
+}
+
+static int mcmc_run_impl(bgp_handle_t h, double* pos_dev, double* lp_dev, int W, int T, double a, uint64_t seed,
+                         double* chain_dev, double* lp_chain_dev, int32_t* accepted_dev, bool sharded, void* stream) {
   if (ready(h)) return -1;
   const int p = h->host_prog.n_theta;
   if (!pos_dev || !lp_dev || W < 2 || W > 8192 || T < 0) return fail("bad mcmc arguments");
@@ -596,14 +728,18 @@ int bgp_mcmc_run(bgp_handle_t h, double* pos_dev, double* lp_dev, int W, int T, 
   *h->seed_pinned = seed;
   CUDA_TRY(cudaMemcpyAsync(h->mc_seed.p, h->seed_pinned, sizeof(uint64_t), cudaMemcpyHostToDevice, st));
   if (st == nullptr) {  // the legacy default stream cannot be captured: run eagerly
-    return mcmc_enqueue(h, pos_dev, lp_dev, W, T, a, chain_dev, lp_chain_dev, accepted_dev, st);
+    return mcmc_enqueue(h, pos_dev, lp_dev, W, T, a, chain_dev, lp_chain_dev, accepted_dev, sharded, st);
   }
-  GraphKey key{pos_dev, lp_dev, chain_dev, lp_chain_dev, accepted_dev, W, T, h->n, h->d, p, a};
+  GraphKey key;
+  std::memset(&key, 0, sizeof(key));   // compared with memcmp: padding bytes must be defined
+  key.pos = pos_dev; key.lp = lp_dev; key.chain = chain_dev; key.lpc = lp_chain_dev; key.acc = accepted_dev;
+  key.W = W; key.T = T; key.n = h->n; key.d = h->d; key.p = p; key.a = a;
+  key.rank = sharded ? h->peers.rank : 0; key.world = sharded ? h->peers.world : 1;
   if (!(h->have_graph && h->key == key)) {
     if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
     h->have_graph = false;
     CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc = mcmc_enqueue(h, pos_dev, lp_dev, W, T, a, chain_dev, lp_chain_dev, accepted_dev, st);
+    int rc = mcmc_enqueue(h, pos_dev, lp_dev, W, T, a, chain_dev, lp_chain_dev, accepted_dev, sharded, st);
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamEndCapture(st, &g);
     if (rc) { if (g) cudaGraphDestroy(g); return -1; }

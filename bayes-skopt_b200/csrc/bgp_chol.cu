@@ -685,16 +685,17 @@ static cudaError_t launch_cluster(const CholArgs& A, int grid, size_t smem, cuda
   return cudaLaunchKernelEx(&cfg, chol_lml_kernel<8, CS>, A);
 }
 
-// opt-in to the large dynamic shared-memory carve-out (must happen outside stream capture)
+// opt-in to the large dynamic shared-memory carve-out (must happen outside stream capture).  The
+// attribute is per function, not per handle: it is raised to the hardware maximum once for every
+// variant, so handles with different n in one process cannot lower each other's limit.
+constexpr int CHOL_SMEM_OPTIN = 227 * 1024;
 cudaError_t prepare_chol(int n) {
-  const size_t smem = chol_smem_bytes(n);
-  if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  if (pick_nw(n) == 4)
-    return cudaFuncSetAttribute(chol_lml_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cudaError_t e = cudaFuncSetAttribute(chol_lml_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(chol_lml_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(chol_lml_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(chol_lml_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (chol_smem_bytes(n) > (size_t)CHOL_SMEM_OPTIN) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(chol_lml_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_OPTIN);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(chol_lml_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_OPTIN);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(chol_lml_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_OPTIN);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(chol_lml_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_OPTIN);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(chol_lml_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_OPTIN);
   return e;
 }
 

@@ -32,6 +32,8 @@ struct CholArgs {
   int dbg_tid;           // thread that records them
 };
 cudaError_t prepare_chol(int n);
+cudaError_t prepare_mcmc();   // one-time opt-ins to large dynamic shared memory (outside capture)
+cudaError_t prepare_acq();
 cudaError_t launch_chol(const CholArgs& A, int grid, int sms, cudaStream_t stream);
 
 struct GramArgs {
@@ -68,8 +70,14 @@ struct SweepArgs {
   const double* fixed_ls;
   double y_mean, y_std;
   int n, d, S, m, R, noise_off;
+  int n_leaves;           // stationary leaves of the program (sizes the scaled-candidate block)
+  double* ks_scratch;     // windowed mode: one k* tile per resident CTA (sweep_scratch_doubles each)
+  long long ks_scratch_stride;
 };
-cudaError_t launch_sweep(const SweepArgs& A, cudaStream_t stream);
+cudaError_t prepare_sweep();
+size_t sweep_scratch_doubles(int n);
+bool sweep_is_windowed(int n, int d, int R, int n_leaves);
+cudaError_t launch_sweep(const SweepArgs& A, int sms, cudaStream_t stream);
 
 struct ExtractArgs {
   const double* slab;
@@ -149,5 +157,17 @@ cudaError_t launch_accept(double* pos, double* lp, const double* q, const double
                           const double* new_lp, const int32_t* movers, int W, int p, int half,
                           uint64_t seed, const uint64_t* seed_ptr, int step, int32_t* accepted,
                           double* chain_step, double* lp_step, cudaStream_t stream);
+
+// peer exchange of walker log-probs (bgp_peer.cu): block[r] = rank r's exchange block as mapped here
+struct PeerXchg {
+  double* block[8];
+  int rank, world, cap;
+};
+cudaError_t launch_xchg_gather(const PeerXchg& X, const double* src, int lo, int cnt, int total, double* out,
+                               cudaStream_t stream);
+cudaError_t launch_accept_xchg(const PeerXchg& X, double* pos, double* lp, const double* q, const double* factors,
+                               const double* new_lp_local, int lo, int cnt, const int32_t* movers, int W, int p,
+                               int half, uint64_t seed, const uint64_t* seed_ptr, int step, int32_t* accepted,
+                               double* chain_step, double* lp_step, cudaStream_t stream);
 
 }  // namespace bgp

@@ -75,12 +75,11 @@ __global__ void propose_kernel(const double* __restrict__ pos, const int32_t* __
 }
 
 // accept k iff factors_k + new_lp_k - lp[movers_k] > log u   (emcee RedBlueMove.propose)
-__global__ void accept_kernel(double* __restrict__ pos, double* __restrict__ lp, const double* __restrict__ q,
-                              const double* __restrict__ factors, const double* __restrict__ new_lp,
-                              const int32_t* __restrict__ movers, int W, int p, int half, uint64_t seed,
-                              const uint64_t* seed_ptr, int step, int32_t* __restrict__ accepted,
-                              double* __restrict__ chain_step, double* __restrict__ lp_step) {
-  const uint64_t sd = seed_of(seed, seed_ptr);
+__device__ void accept_body(double* __restrict__ pos, double* __restrict__ lp, const double* __restrict__ q,
+                            const double* __restrict__ factors, const double* __restrict__ new_lp,
+                            const int32_t* __restrict__ movers, int W, int p, int half, uint64_t sd, int step,
+                            int32_t* __restrict__ accepted, double* __restrict__ chain_step,
+                            double* __restrict__ lp_step) {
   for (int k = threadIdx.x; k < W; k += blockDim.x) {
     const int i = movers[k];
     if (i < 0) continue;
@@ -97,6 +96,21 @@ __global__ void accept_kernel(double* __restrict__ pos, double* __restrict__ lp,
     for (int e = threadIdx.x; e < W * p; e += blockDim.x) chain_step[e] = pos[e];
     if (lp_step) for (int e = threadIdx.x; e < W; e += blockDim.x) lp_step[e] = lp[e];
   }
+}
+
+__global__ void accept_kernel(double* __restrict__ pos, double* __restrict__ lp, const double* __restrict__ q,
+                              const double* __restrict__ factors, const double* __restrict__ new_lp,
+                              const int32_t* __restrict__ movers, int W, int p, int half, uint64_t seed,
+                              const uint64_t* seed_ptr, int step, int32_t* __restrict__ accepted,
+                              double* __restrict__ chain_step, double* __restrict__ lp_step) {
+  accept_body(pos, lp, q, factors, new_lp, movers, W, p, half, seed_of(seed, seed_ptr), step, accepted, chain_step,
+              lp_step);
+}
+
+// split_kernel keeps W 64-bit sort keys in dynamic shared memory: opt in above the 48 KB default so
+// that the W <= 8192 the API accepts really launches (outside stream capture, from bgp_create)
+cudaError_t prepare_mcmc() {
+  return cudaFuncSetAttribute(split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * (int)sizeof(uint64_t));
 }
 
 cudaError_t launch_split(int W, uint64_t seed, const uint64_t* seed_ptr, int step, int32_t* colour,
@@ -119,5 +133,102 @@ cudaError_t launch_accept(double* pos, double* lp, const double* q, const double
                                         step, accepted, chain_step, lp_step);
   return cudaGetLastError();
 }
+
+// ---------------------------------------------------------------------------- multi-GPU
+// Walker sharding without the host: the log-probabilities of a half step are exchanged by
+// plain stores into every peer's exchange block (cudaIpc-mapped, NVLink P2P through NVSwitch) plus a
+// release flag per source rank; the accept kernel acquires on the flags.  No NCCL call and no host
+// round trip sits between propose and accept, so the whole sharded run is one CUDA graph per rank.
+//
+// Exchange block of a rank (bgp_peer_export allocates it with cudaMalloc; every peer maps it):
+//   [0, 2 cap)      doubles   two value buffers (epoch parity): slot i = log-prob of proposal i
+//   then 8 + 8 u64            flags[src] = last epoch whose slice from rank `src` is complete;
+//                             word 8 = this rank's own epoch counter, word 9 = time-out flag
+// A rank may run at most one epoch ahead of a peer (it cannot pass the wait of epoch e + 1 before the
+// peer has published e + 1, which the peer does after it finished reading the buffer of epoch e), so
+// two buffers are enough.
+// Replaces the `ncclAllGather of (W/2G) log-probs` of SURVEY.md 8(e) / emcee's serial map over walkers
+// (bask/bayesgpr.py:510-530).
+
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
+
+// Publishes src[0, cnt) as slots [lo, lo + cnt) of the current epoch to every rank, waits until every
+// rank's slice has arrived here, and returns this rank's complete buffer.  Called by all threads of a
+// single-CTA kernel.
+__device__ const double* peer_exchange(const PeerXchg& X, const double* __restrict__ src, int lo, int cnt) {
+  __shared__ unsigned long long ep_s;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  unsigned long long* my_words = reinterpret_cast<unsigned long long*>(X.block[X.rank] + 2 * (size_t)X.cap);
+  if (tid == 0) ep_s = my_words[8] + 1;
+  __syncthreads();
+  const unsigned long long ep = ep_s;
+  const size_t par = (size_t)(ep & 1) * X.cap;
+  for (int peer = 0; peer < X.world; ++peer) {
+    double* dst = X.block[peer] + par + lo;
+    for (int i = tid; i < cnt; i += nt) dst[i] = src[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < X.world) {
+    unsigned long long* peer_words = reinterpret_cast<unsigned long long*>(X.block[tid] + 2 * (size_t)X.cap);
+    st_release_sys(peer_words + X.rank, ep);
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(my_words + tid) < ep) {
+      if (global_ns() - t0 > 10000000000ULL) { my_words[9] = 1; break; }   // 10 s: a peer died; do not hang the GPU
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) my_words[8] = ep;
+  return X.block[X.rank] + par;
+}
+
+// all W initial log-probs: lp[i] = exchanged value i
+__global__ void xchg_gather_kernel(PeerXchg X, const double* __restrict__ src, int lo, int cnt, int total,
+                                   double* __restrict__ out) {
+  const double* all = peer_exchange(X, src, lo, cnt);
+  for (int i = threadIdx.x; i < total; i += blockDim.x) out[i] = all[i];
+}
+
+// accept with the exchange in front: new_lp_local holds this rank's slice [lo, lo + cnt) of the half step
+__global__ void accept_xchg_kernel(PeerXchg X, double* __restrict__ pos, double* __restrict__ lp,
+                                   const double* __restrict__ q, const double* __restrict__ factors,
+                                   const double* __restrict__ new_lp_local, int lo, int cnt,
+                                   const int32_t* __restrict__ movers, int W, int p, int half, uint64_t seed,
+                                   const uint64_t* seed_ptr, int step, int32_t* __restrict__ accepted,
+                                   double* __restrict__ chain_step, double* __restrict__ lp_step) {
+  const double* new_lp = peer_exchange(X, new_lp_local, lo, cnt);
+  accept_body(pos, lp, q, factors, new_lp, movers, W, p, half, seed_ptr ? *seed_ptr : seed, step, accepted,
+              chain_step, lp_step);
+}
+
+cudaError_t launch_xchg_gather(const PeerXchg& X, const double* src, int lo, int cnt, int total, double* out,
+                               cudaStream_t stream) {
+  xchg_gather_kernel<<<1, 256, 0, stream>>>(X, src, lo, cnt, total, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_accept_xchg(const PeerXchg& X, double* pos, double* lp, const double* q, const double* factors,
+                               const double* new_lp_local, int lo, int cnt, const int32_t* movers, int W, int p,
+                               int half, uint64_t seed, const uint64_t* seed_ptr, int step, int32_t* accepted,
+                               double* chain_step, double* lp_step, cudaStream_t stream) {
+  accept_xchg_kernel<<<1, 256, 0, stream>>>(X, pos, lp, q, factors, new_lp_local, lo, cnt, movers, W, p, half, seed,
+                                            seed_ptr, step, accepted, chain_step, lp_step);
+  return cudaGetLastError();
+}
+
 
 }  // namespace bgp

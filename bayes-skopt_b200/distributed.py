@@ -1,32 +1,40 @@
-"""Multi-GPU orchestration of the candidate sweep: one process per GPU (torch.distributed,
-NCCL over NVLink on the B200 box; gloo in the CPU tests).
+"""Multi-GPU orchestration: one process per GPU (torch.distributed for the plumbing; NCCL over NVLink
+on the B200 box, gloo in the CPU tests).
 
-What shards: the candidate points.  Every rank holds the (tiny) training
-set, factorises the same S sampled thetas, sweeps only its contiguous block of candidates and
-exchanges per-theta scalars:
+What shards:
+
+* the WALKERS of the ensemble MCMC: every rank regenerates the identical red/blue split, proposals and
+  accept draws from the shared Philox stream, evaluates the log-posterior of its slice of each half
+  step's proposals and stores the results straight into every peer's exchange block (cudaIpc-mapped
+  memory, NVLink P2P) -- no NCCL call and no host round trip between propose and accept, so the whole
+  run is ONE CUDA graph per rank (``Engine.mcmc_sharded`` -> ``bgp_mcmc_run_sharded``).  When the peer
+  mapping is not available the same move runs host-stepped with one NCCL all-gather per half step.
+* the CANDIDATES of the acquisition sweep: every rank holds the (tiny) training set, factorises the same
+  S sampled thetas, sweeps only its contiguous block of candidates and exchanges per-theta scalars:
 
   EI        all-reduce(MIN) of the per-theta minimum mean                      S doubles
   TopTwoEI  all-gather of each rank's best (EI, index, mu, sd) per theta       4 S doubles / rank
-  MES       all-gather of the (S x m_local) moments, after which every rank repeats the
-            (cheap) Gumbel quantile search on the full set -- instead of ~13 rounds of scalar
-            all-reduces, one bandwidth-trivial collective
+  MES       all-gather of the (S x m_local) moments; the Gumbel fit is then split over thetas (every
+            rank fits its share on all candidates -- the same bits as a one-GPU fit) and the five fit
+            parameters per theta are gathered
   all       all-reduce(MAX) of the per-theta "non-finite" flags (bask/acquisition.py:140-141
             skips a theta if ANY candidate is non-finite), then all-gather of the m_local values.
 
-What does not shard: the joint posterior draw behind ThompsonSampling / PVRS (one m x m
-factorisation) -- replicas only; and the MCMC at the headline sizes, where W/2 = 64 log-posteriors
-per half step do not even fill one GPU, so every rank replays the identical Philox stream and no
-walker collective is needed.
+  Every kernel and collective of a sweep is enqueued on the engine's stream; the host synchronises once,
+  at the end.
 
-The numerical steps are injected through a small backend protocol so that the orchestration
-(this file) is exercised on CPU with gloo, using the oracle as the stand-in compute."""
+What does not shard: the joint posterior draw behind ThompsonSampling / PVRS (one m x m factorisation)
+-- replicas only.
+
+The numerical steps are injected through a small backend protocol so that the orchestration (this file)
+is exercised on CPU with gloo, using the oracle as the stand-in compute."""
 import numpy as np
 import torch
 import torch.distributed as dist
 
 from . import _lib
 
-__all__ = ["shard_bounds", "ShardedSweep", "DeviceBackend", "sharded_mcmc"]
+__all__ = ["shard_bounds", "ShardedSweep", "DeviceBackend", "sharded_mcmc", "sharded_mcmc_dev"]
 
 
 def shard_bounds(m, world, rank):
@@ -54,27 +62,29 @@ class DeviceBackend:
         e = self.e
         th = thetas if torch.is_tensor(thetas) else e.to_dev(thetas)
         f = e.factorize(th)
-        if np.any(e.to_host(f.info) != 0):
-            raise np.linalg.LinAlgError("The kernel is not returning a positive definite matrix.")
+        self._pending_info = f.info       # read back once, in finalize(): no host round trip in the sweep
         y_mean = float(np.atleast_1d(self.gpr.y_train_mean_)[0])
         y_std = float(np.atleast_1d(self.gpr.y_train_std_)[0])
         Xd = X_block.contiguous() if torch.is_tensor(X_block) else e.to_dev(X_block)
         mu, sd, _, _ = e.predict(f, Xd, noise_off=True, y_mean=y_mean, y_std=y_std)
-        e.sync()
         return mu, sd
+
+    def finalize(self):
+        """The single host synchronisation of a sweep: positive-definiteness flags of the factorisations."""
+        info, self._pending_info = getattr(self, "_pending_info", None), None
+        if info is not None and np.any(self.e.to_host(info) != 0):
+            raise np.linalg.LinAlgError("The kernel is not returning a positive definite matrix.")
 
     def min_mu(self, mu, sd):
         S, m = mu.shape
         stats = self.e.empty(S, 4)
         self._run(self.e.lib.bgp_acq_stats, mu.data_ptr(), sd.data_ptr(), S, m, stats.data_ptr())
-        self.e.sync()
         return stats[:, 0].contiguous()
 
     def mes_fit(self, mu_all, sd_all):
         S, m = mu_all.shape
         fit = self.e.empty(S, 5)
         self._run(self.e.lib.bgp_mes_fit, mu_all.data_ptr(), sd_all.data_ptr(), S, m, fit.data_ptr())
-        self.e.sync()
         return fit
 
     def ei_best(self, mu, sd, p0, yopt, index_offset):
@@ -82,7 +92,6 @@ class DeviceBackend:
         ref = self.e.empty(S, 4)
         self._run(self.e.lib.bgp_ei_best, mu.data_ptr(), sd.data_ptr(), S, m, float(p0),
                   None if yopt is None else yopt.data_ptr(), int(index_offset), ref.data_ptr())
-        self.e.sync()
         return ref
 
     def per_theta(self, kind, mu, sd, p0, yopt=None, ref=None, gumbel=None, fit=None):
@@ -94,14 +103,12 @@ class DeviceBackend:
                   None if yopt is None else yopt.data_ptr(), None if ref is None else ref.data_ptr(),
                   None if g is None else g.data_ptr(), 0 if g is None else g.shape[1],
                   None if fit is None else fit.data_ptr(), vals.data_ptr(), skipped.data_ptr())
-        self.e.sync()
         return vals, skipped
 
     def combine(self, vals, skipped):
         S, m = vals.shape
         out = self.e.empty(m)
         self._run(self.e.lib.bgp_acq_combine, vals.data_ptr(), S, m, skipped.data_ptr(), out.data_ptr())
-        self.e.sync()
         return out
 
 
@@ -128,7 +135,11 @@ class ShardedSweep:
     def evaluate(self, X, thetas, acquisitions, gumbels=None):
         """See _evaluate; every tensor op and collective is issued on the backend's stream."""
         with self.b.stream_ctx():
-            return self._evaluate(X, thetas, acquisitions, gumbels)
+            out = self._evaluate(X, thetas, acquisitions, gumbels)
+        fin = getattr(self.b, "finalize", None)
+        if fin is not None and not self.keep_on_device:
+            fin()
+        return out
 
     def _evaluate(self, X, thetas, acquisitions, gumbels=None):
         """X: (m, d) all candidates (same on every rank); thetas: (S, p) sampled hyper-parameters;
@@ -199,12 +210,39 @@ class ShardedSweep:
         return out_dev if self.keep_on_device else out
 
 
-def sharded_mcmc(engine, pos, n_steps, seed, a, group, lp_extra_fn=None):
-    """Walker-sharded stretch move: every rank regenerates the identical red/blue split,
-    proposals and accept draws from the shared Philox stream (no broadcast), evaluates the
-    log-posterior of ITS slice of the W/2 proposals of each half step, and one all-gather of
-    W/2 doubles per half step makes the accept test identical everywhere.  Returns host
-    (chain_steps (T, W, p), final pos (W, p), acceptance counts (W,))."""
+def sharded_mcmc_dev(engine, pos, n_steps, seed, a, group, buffers=None):
+    """Walker-sharded stretch move, device resident: returns the engine's MCMC buffers (pos, lp, chain,
+    lpc, acc tensors), identical on every rank.  One CUDA graph per rank with peer stores for the
+    log-prob exchange; falls back to the host-stepped NCCL variant when the exchange blocks cannot be
+    mapped (no P2P between the GPUs)."""
+    e = engine
+    if getattr(e, "_no_peer_access", False):
+        return _sharded_mcmc_nccl(e, pos, n_steps, seed, a, group)
+    try:
+        return e.mcmc_sharded(pos, n_steps, seed, group, a=a, buffers=buffers)
+    except _lib.BgpError as exc:
+        if "cudaIpc" not in str(exc):
+            raise
+        import warnings
+        warnings.warn(f"peer mapping unavailable ({exc}); the sharded MCMC runs host-stepped over NCCL")
+        e._no_peer_access = True
+        return _sharded_mcmc_nccl(e, pos, n_steps, seed, a, group)
+
+
+def sharded_mcmc(engine, pos, n_steps, seed, a, group):
+    """Host-facing wrapper of ``sharded_mcmc_dev``: (chain_steps (T, W, p), final pos (W, p), acceptance
+    counts (W,)) as numpy arrays."""
+    b = sharded_mcmc_dev(engine, pos, n_steps, seed, a, group, buffers=getattr(engine, "_mc_buffers_sharded", None))
+    engine._mc_buffers_sharded = b
+    engine.sync()
+    if getattr(engine, "_peers", None) is not None and engine.peer_timed_out():
+        raise RuntimeError("a rank of the process group did not answer within 10 s during the sharded MCMC")
+    return b["chain"].cpu().numpy(), b["pos"].cpu().numpy(), b["acc"].cpu().numpy()
+
+
+def _sharded_mcmc_nccl(engine, pos, n_steps, seed, a, group):
+    """The same move with the log-probs exchanged by one all-gather of W/2 doubles per half step (host
+    stepped: 5 launches + 1 collective per half step)."""
     import ctypes as C
     e = engine
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -213,7 +251,7 @@ def sharded_mcmc(engine, pos, n_steps, seed, a, group, lp_extra_fn=None):
     P = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
     sd = C.c_uint64(int(seed) & (2 ** 64 - 1))
     with torch.cuda.stream(e.stream):
-        d_pos = e.to_dev(pos)
+        d_pos = (pos if torch.is_tensor(pos) else e.to_dev(pos)).clone()
         lo, hi = shard_bounds(W, world, rank)
         sizes = [shard_bounds(W, world, r)[1] - shard_bounds(W, world, r)[0] for r in range(world)]
         lp_loc, _, _ = e.logprob_dev(d_pos[lo:hi].contiguous())
@@ -238,8 +276,7 @@ def sharded_mcmc(engine, pos, n_steps, seed, a, group, lp_extra_fn=None):
                                                t, P(acc), P(chain[t]) if half == 1 else None,
                                                P(lpc[t]) if half == 1 else None, st), "bgp_mcmc_accept")
                 e.launches += 5
-        e.sync()
-        return chain.cpu().numpy(), d_pos.cpu().numpy(), acc.cpu().numpy()
+    return dict(pos=d_pos, lp=d_lp, chain=chain, lpc=lpc, acc=acc)
 
 
 def _allgather_1d(t, sizes, group):

@@ -217,7 +217,7 @@ class Optimizer:
         seed -- what expected_optimality_gap issues dozens of times) are answered from a cache."""
         key = None
         if isinstance(random_state, (int, np.integer)):
-            key = (len(self.Xi), id(self.gp.chain_), int(random_state), int(n_random_starts))
+            key = (len(self.Xi), getattr(self.gp, "chain_generation_", id(self.gp.chain_)), int(random_state), int(n_random_starts))
             if getattr(self, "_expected_optimum_cache", (None, None))[0] == key:
                 return self._expected_optimum_cache[1]
         result = create_result(self.Xi, self.yi, self.space, self.rng, models=[self.gp])

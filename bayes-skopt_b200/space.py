@@ -86,6 +86,16 @@ class Categorical(Dimension):
     def __init__(self, categories, prior=None, transform="normalize", name=None):
         self.categories, self.prior, self.name = tuple(categories), prior, name
 
+    def rvs(self, n_samples=1, random_state=None):
+        """Categories drawn with probability ``prior`` (uniform when None) by inverting the discrete
+        CDF on one uniform per sample -- what skopt's rv_discrete-based Categorical does.  (The
+        inherited rounding of a uniform on [0, 1] would halve the mass of the first and last category.)"""
+        rng = check_random_state(random_state)
+        k = len(self.categories)
+        p = np.full(k, 1.0 / k) if self.prior is None else np.asarray(self.prior, dtype=float)
+        idx = np.minimum(np.searchsorted(np.cumsum(p), rng.uniform(size=n_samples), side="left"), k - 1)
+        return [self.categories[i] for i in idx]
+
     def transform(self, X):
         idx = np.array([self.categories.index(x) for x in X], dtype=float)
         return idx / max(len(self.categories) - 1, 1)

@@ -6,18 +6,27 @@ evaluations, warm-started like Optimizer.tell's 2nd+ call), then the MaxValueSea
 10 theta samples x 10 000 candidates and the argmax.  One "step" = one such sample()+ask() cycle.
 
 value  : LML evaluations per second over the whole cycle, inputs resident in HBM
-         (1 536 * n_gpus_cycles / cycle time; the sweep's time is charged to it on purpose, so
-         the ratio against the reference arm is the cycle speed-up the north star asks for).
+         (1 536 * n_gpus / cycle time; the sweep's time is charged to it on purpose, so the
+         ratio against the reference arm is the cycle speed-up the north star asks for).
 e2e    : the same through the public API (BayesGPR.sample + evaluate_acquisitions + argmax) with
          numpy inputs: H2D of X, y, noise, candidates and Gumbel variates, D2H of the chain,
          walker positions and acquisition values inside the timed region.
+Both halves of BASELINE.json's metric are also reported on their own: `lml_evals_per_s_batched`
+(1 024 thetas per launch, n=500) and `ask_latency_ms` (evaluate_acquisitions + argmax, host in/out).
 
---impl reference times the CPU restatement of the reference path (oracle/, kind "port":
-scikit-optimize and emcee are not installable here) on the host cores, on a bounded sample.
+Beside the headline line:
+  c5            BASELINE configs[4] (Ackley-20, n=2000, 100 000 candidates, 16 thetas, EI + MES): the
+                sweep on this run's N GPUs (candidates sharded) and on ONE GPU in the same run, the
+                strong-scaling efficiency, and whether both give the same argmax / values
+  small_configs configs[0] and configs[1] cycle times with the CPU port beside them (N=1 only)
+
+--impl reference times COMPLETE C3 cycles of the CPU restatement of the reference path (oracle/,
+kind "port": scikit-optimize and emcee are not installable here) on the host cores: every timed
+step is one full sample() of 1 536 log-posteriors plus the full 10 x 10 000 MES sweep -- nothing
+is extrapolated.  Warm-up steps (untimed) are 1/8-size cycles.
 """
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys
@@ -36,6 +45,7 @@ os.dup2(2, 1)
 def emit(line):
     sys.stdout.flush()
     os.write(_STDOUT_FD, (json.dumps(line) + "\n").encode())
+
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
@@ -103,48 +113,57 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------ CPU arm
-def cpu_reference_cycle(w, lml_evals=48, sweep_thetas=1, sweep_cands=400, seed=0):
-    """Times the oracle (CPU port of the reference path) on a bounded sample of the workload and
-    extrapolates to the full cycle.  Returns (cycle_seconds_estimate, detail dict)."""
-    from oracle import acq_oracle as A
-    from oracle import gp_oracle as G
-    spec = ("sum", ("product", ("const", 1.0, False), ("matern", 0.3 * np.ones(w.d), 2.5, False)),
+def _default_spec(d):
+    return ("sum", ("product", ("const", 1.0, False), ("matern", 0.3 * np.ones(d), 2.5, False)),
             ("white", 1.0, False))
-    priors = G.guess_priors(spec)
-    y = (w.y - w.y.mean()) / w.y.std()
-    alpha = 1e-10 * np.ones(w.n) + w.noise_vector
-    rng = np.random.RandomState(seed)
-    thetas = W.centre_theta(w.d) + 0.05 * rng.randn(lml_evals, w.d + 2)
-    t0 = time.perf_counter()
-    for t in thetas:
-        G.log_prob(spec, t, w.X, y, alpha, priors)
-    t_lml = (time.perf_counter() - t0) / lml_evals
-    gp = A.GPState(spec=spec, X=w.X, y=y, alpha=alpha, chain=thetas, theta=thetas[0].copy(),
-                   y_mean=float(w.y.mean()), y_std=float(w.y.std()))
-    Xc = w.candidates[:sweep_cands]
-    t0 = time.perf_counter()
-    for s in range(sweep_thetas):
-        gp.set_theta(thetas[s])
-    t_setter = (time.perf_counter() - t0) / sweep_thetas
-    t0 = time.perf_counter()
-    for s in range(sweep_thetas):
-        mu, sd = G.predict(spec, thetas[s], w.X, Xc, gp.K_inv, gp.a, gp.y_mean, gp.y_std)
-    t_pred = (time.perf_counter() - t0) / sweep_thetas / sweep_cands
-    t0 = time.perf_counter()
-    with np.errstate(all="ignore"):
-        if w.acquisition == "mes":
-            A.max_value_search(mu, sd, n_min_samples=w.acq_kwargs.get("n_min_samples", 1000),
-                               uniforms=rng.rand(w.acq_kwargs.get("n_min_samples", 1000)).astype(np.float32))
+
+
+class CpuCycle:
+    """The reference's sample() + ask() tail on the host cores, restated in oracle/ (kind "port")."""
+
+    def __init__(self, w, seed=0):
+        from oracle import acq_oracle as A
+        from oracle import cycle_oracle as C
+        from oracle import gp_oracle as G
+        self.A, self.C, self.G, self.w = A, C, G, w
+        self.spec = _default_spec(w.d)
+        self.priors = G.guess_priors(self.spec)
+        y = (w.y - w.y.mean()) / w.y.std()
+        alpha = 1e-10 * np.ones(w.n) + w.noise_vector
+        rng = np.random.RandomState(seed)
+        # warm start: walkers in a ball around a plausible point estimate (what tell()'s 2nd+ call sees)
+        self.pos = W.centre_theta(w.d) + 0.05 * rng.randn(w.n_walkers, w.d + 2)
+        self.gp = A.GPState(spec=self.spec, X=w.X, y=y, alpha=alpha, chain=self.pos.copy(),
+                            theta=self.pos[0].copy(), y_mean=float(w.y.mean()), y_std=float(w.y.std()))
+        self.rng = rng
+
+    def run(self, n_steps=None, n_cand=None, n_theta=None):
+        """One cycle; the defaults are the full workload.  Returns (sample_s, ask_s, n_logprob_evals)."""
+        w = self.w
+        T = w.n_steps if n_steps is None else n_steps
+        m = len(w.candidates) if n_cand is None else n_cand
+        S = w.n_theta_samples if n_theta is None else n_theta
+        t0 = time.perf_counter()
+        pos, _lp, evals = self.C.sample(self.gp, self.priors, self.rng, n_desired_samples=w.n_walkers,
+                                        n_burnin=T - 1, n_walkers=w.n_walkers, position=self.pos)
+        t1 = time.perf_counter()
+        if w.acquisition == "pvrs":
+            np.random.seed(w.mes_seed)
+            self.C.ask_tail(w.candidates[:m], self.gp, "pvrs", 0, self.rng, **w.acq_kwargs)
         else:
-            A.UNCERTAINTY_FN[w.acquisition](mu, sd)
-    t_acq = (time.perf_counter() - t0) / sweep_cands
-    m, S = len(w.candidates), w.n_theta_samples
-    t_sample = w.n_logprob_evals * t_lml
-    t_ask = S * (t_setter + m * (t_pred + t_acq))
-    detail = {"lml_eval_ms": 1e3 * t_lml, "theta_setter_ms": 1e3 * t_setter,
-              "predict_us_per_candidate": 1e6 * t_pred, "acq_us_per_candidate": 1e6 * t_acq,
-              "sample_s_extrapolated": t_sample, "ask_s_extrapolated": t_ask}
-    return t_sample + t_ask, detail
+            np.random.seed(w.mes_seed)
+            self.C.ask_tail(w.candidates[:m], self.gp, w.acquisition, S, self.rng, **w.acq_kwargs)
+        t2 = time.perf_counter()
+        self.pos = pos
+        return t1 - t0, t2 - t1, evals
+
+
+def _threads_in_use():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count()
 
 
 def run_reference(args):
@@ -152,35 +171,203 @@ def run_reference(args):
     if rank != 0:
         return
     w = W.config3()
-    times, detail = [], None
-    # bounded sample per step, sized so that the whole run takes about 75 s of CPU time
-    # (BGP_BENCH_REF_BUDGET_S overrides the total, used by the CPU test of the output contract)
-    budget = float(os.environ.get("BGP_BENCH_REF_BUDGET_S", "75")) / max(1, args.warmup + args.steps)
-    n_lml = int(min(256, max(16, budget * 0.4 / 0.006)))
-    n_cand = int(min(2000, max(200, budget * 0.5 / 0.00045)))
-    for i in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        cyc, detail = cpu_reference_cycle(w, lml_evals=n_lml, sweep_thetas=1, sweep_cands=n_cand, seed=i)
-        if i >= args.warmup:
-            times.append(cyc)
-        detail["sample_wall_s"] = time.perf_counter() - t0
-    cyc = float(np.mean(times))
-    value = w.n_logprob_evals / cyc
-    sample = (f"per step: {n_lml} log-posterior evals + 1 theta-setter + predict/MES over {n_cand} candidates at "
-              "n=500, extrapolated linearly to 1536 evals + 10 thetas x 10000 candidates")
+    cyc = CpuCycle(w)
+    # BGP_BENCH_REF_BUDGET_S (the CPU test of the output contract sets it) shrinks the cycle so the
+    # contract can be checked in seconds; the default is the complete workload
+    budget = os.environ.get("BGP_BENCH_REF_BUDGET_S")
+    full = budget is None
+    shrink = dict() if full else dict(n_steps=1, n_cand=200, n_theta=1)
+    for _ in range(args.warmup):
+        cyc.run(n_steps=2, n_cand=1250, n_theta=2) if full else cyc.run(**shrink)
+    t_sample, t_ask, evals = [], [], 0
+    for _ in range(args.steps):
+        a, b, evals = cyc.run(**shrink)
+        t_sample.append(a); t_ask.append(b)
+    cycle_s = float(np.mean(t_sample) + np.mean(t_ask))
+    value = evals / cycle_s
+    one_thread = None
+    if full and not args.no_single_thread:
+        try:
+            from threadpoolctl import threadpool_limits
+            with threadpool_limits(limits=1):
+                a, b, ev = cyc.run()
+            one_thread = {"cycle_s": a + b, "sample_s": a, "ask_s": b, "value": ev / (a + b)}
+        except Exception as exc:       # noqa: BLE001
+            one_thread = {"error": str(exc)}
+    sample = ("every timed step is one complete cycle: sample() with %d walkers x %d steps = %d log-posterior "
+              "evaluations, then MaxValueSearch over %d thetas x %d candidates; warm-up steps are 1/8-size cycles"
+              % (w.n_walkers, w.n_steps, evals, w.n_theta_samples, len(w.candidates))) if full else \
+             "contract-test shrink (BGP_BENCH_REF_BUDGET_S set): 1 MCMC step, 1 theta x 200 candidates"
+    cores = _threads_in_use()
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * cyc, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * cycle_s, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": w.name, "n_obs": w.n, "dims": w.d, "walkers": w.n_walkers,
                        "mcmc_steps": w.n_steps, "theta_samples": w.n_theta_samples,
-                       "candidates": len(w.candidates), "acquisition": w.acquisition},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                             "sample": sample, "detail": detail},
+                       "candidates_per_gpu": len(w.candidates), "acquisition": w.acquisition},
+            "lml_evals_per_s_batched": evals / float(np.mean(t_sample)),
+            "ask_latency_ms": 1e3 * float(np.mean(t_ask)),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "sample_s": float(np.mean(t_sample)), "ask_s": float(np.mean(t_ask)),
+                             "omp_num_threads_1": one_thread},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
 
 # ------------------------------------------------------------------------------ GPU arm
+def _timed(e, fn, reps, warm=1):
+    """CUDA-event milliseconds per call of fn() on the engine's stream."""
+    import torch
+    for _ in range(warm):
+        fn()
+    e.sync()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(e.stream)
+    for _ in range(reps):
+        fn()
+    b.record(e.stream)
+    e.sync()
+    return a.elapsed_time(b) / reps
+
+
+def bench_c5(args, rank, world, local, pg):
+    """BASELINE configs[4]: 20-D Ackley, n=2000, 256 walkers, 100 000 candidates, 16 thetas, EI + MES.
+    Strong scaling of the candidate sweep: the same 100 000 candidates on this run's N GPUs and (rank 0)
+    on one GPU, in the same process, with the results compared."""
+    import torch
+    import torch.distributed as dist
+
+    import bask_b200
+    from bask_b200 import _lib
+    from bask_b200.distributed import DeviceBackend, ShardedSweep
+    from bask_b200.utils import construct_default_kernel
+
+    w = W.config5(m=args.c5_candidates, acquisition="mes")
+    S, K = w.n_theta_samples, 1000
+    gp = bask_b200.BayesGPR(kernel=construct_default_kernel(list(range(w.d))), normalize_y=True, random_state=0,
+                            device=local)
+    t0 = time.perf_counter()
+    gp.fit(w.X, w.y, noise_vector=w.noise_vector, n_desired_samples=w.n_walkers, n_burnin=w.n_burnin,
+           n_walkers_per_thread=w.n_walkers, progress=False, process_group=pg)
+    fit_s = time.perf_counter() - t0
+    e = gp._eng()
+    # warm-started sample(): 256 walkers x 11 steps at n=2000 (walkers sharded over the ranks)
+    e.sync()
+    t0 = time.perf_counter()
+    gp.sample(n_desired_samples=w.n_walkers, n_burnin=w.n_burnin, n_walkers_per_thread=w.n_walkers, process_group=pg)
+    e.sync()
+    mcmc_ms = 1e3 * (time.perf_counter() - t0)
+    picks = np.random.RandomState(1).choice(len(gp.chain_), replace=False, size=S)
+    th = e.to_dev(gp.chain_[picks])
+    Xc = e.to_dev(w.candidates)
+    g32 = e.to_dev(np.stack([bask_b200.acquisition.gumbel32_like_reference(K) for _ in range(S)]),
+                   dtype=torch.float32)
+    y_mean, y_std = float(gp.y_train_mean_), float(gp.y_train_std_)
+    spec = [(_lib.ACQ_EI, float("nan")), (_lib.ACQ_MES, float("nan"))]
+
+    def single():
+        f = e.factorize(th)
+        mu, sd, _, _ = e.predict(f, Xc, noise_off=True, y_mean=y_mean, y_std=y_std)
+        ei, _, _, _ = e.acq(_lib.ACQ_EI, mu, sd)
+        mes, _, _, _ = e.acq(_lib.ACQ_MES, mu, sd, gumbel32=g32)
+        return ei, mes, e.argmax(ei), e.argmax(mes)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    out = {"workload": w.name, "n_obs": w.n, "dims": w.d, "walkers": w.n_walkers, "theta_samples": S,
+           "candidates": len(w.candidates), "acquisitions": ["ei", "mes"], "scaling": "strong",
+           "fit_s": fit_s, "mcmc_ms": mcmc_ms, "mcmc_logprob_evals": w.n_logprob_evals}
+    reps = args.c5_reps
+    # one GPU, all candidates (rank 0 only; the other ranks wait at the barrier)
+    barrier()
+    if rank == 0:
+        one_ms = _timed(e, single, reps)
+        ei1, mes1, a_ei1, a_mes1 = single()
+        # the sweep kernel alone, for the roofline of the n=2000 path
+        f = e.factorize(th)
+        k_ms = _timed(e, lambda: e.predict(f, Xc, noise_off=True, y_mean=y_mean, y_std=y_std), max(1, reps // 2))
+        out["sweep_ms_1gpu"] = one_ms
+        out["sweep_kernel_ms_1gpu"] = k_ms
+        out["sweep_kernel_tflops"] = S * len(w.candidates) * flops_sweep(w.n, w.d) / (k_ms * 1e-3) / 1e12
+        del f
+    barrier()
+    if world == 1:
+        out.update(sweep_ms=out["sweep_ms_1gpu"], efficiency_vs_1gpu=1.0, sharded_equals_single=None)
+        return out
+    sweep = ShardedSweep(DeviceBackend(gp), pg, keep_on_device=True)
+
+    def sharded():
+        ei, mes = sweep.evaluate(Xc, th, spec, {1: g32})
+        return ei, mes, e.argmax(ei.contiguous()), e.argmax(mes.contiguous())
+
+    for _ in range(2):
+        sharded()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(e.stream)
+    for _ in range(reps):
+        sharded()
+    b.record(e.stream)
+    barrier()
+    t = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device=e.device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    eiN, mesN, a_eiN, a_mesN = sharded()
+    barrier()
+    out["sweep_ms"] = float(t.cpu())
+    if rank == 0:
+        ei1h, mes1h, eiNh, mesNh = [e.to_host(v) for v in (ei1, mes1, eiN, mesN)]
+        rel = lambda x, y: float(np.max(np.abs(x - y) / np.maximum(np.abs(y), 1e-300)))  # noqa: E731
+        same = (int(e.to_host(a_ei1)[0]) == int(e.to_host(a_eiN)[0])
+                and int(e.to_host(a_mes1)[0]) == int(e.to_host(a_mesN)[0]))
+        out.update(efficiency_vs_1gpu=out["sweep_ms_1gpu"] / (world * out["sweep_ms"]),
+                   sharded_equals_single={"argmax_equal": bool(same), "ei_max_rel_diff": rel(eiNh, ei1h),
+                                          "mes_max_rel_diff": rel(mesNh, mes1h),
+                                          "argmax_ei": int(e.to_host(a_eiN)[0]), "argmax_mes": int(e.to_host(a_mesN)[0])})
+        if not same:
+            raise SystemExit("c5: the sharded sweep and the single-GPU sweep disagree on the argmax")
+    return out
+
+
+def bench_small_configs(args):
+    """configs[0] (Branin n=20, EI, 500 candidates) and configs[1] (Hartmann-6 n=100, PVRS, 1000
+    candidates): one warm-started cycle through the public API, with the CPU port beside it."""
+    import bask_b200
+    from bask_b200.utils import construct_default_kernel
+    res = {}
+    for tag, w in (("c1", W.config1()), ("c2", W.config2())):
+        gp = bask_b200.BayesGPR(kernel=construct_default_kernel(list(range(w.d))), normalize_y=True, random_state=0)
+        gp.fit(w.X, w.y, noise_vector=w.noise_vector, n_desired_samples=w.n_walkers, n_burnin=w.n_burnin,
+               n_walkers_per_thread=w.n_walkers, progress=False)
+        acq = bask_b200.optimizer.ACQUISITION_FUNC[w.acquisition]
+
+        def cycle(seed):
+            gp.sample(w.X, w.y, noise_vector=w.noise_vector, n_desired_samples=w.n_walkers, n_burnin=w.n_burnin,
+                      n_walkers_per_thread=w.n_walkers)
+            v = bask_b200.evaluate_acquisitions(w.candidates, gp, (acq,), n_samples=w.n_theta_samples,
+                                                random_state=seed, **w.acq_kwargs)[0]
+            return int(np.argmax(v))
+
+        for i in range(3):
+            cycle(i)
+        t0 = time.perf_counter()
+        reps = 10
+        for i in range(reps):
+            cycle(10 + i)
+        gpu_ms = 1e3 * (time.perf_counter() - t0) / reps
+        cpu = CpuCycle(w)
+        cpu.run()
+        a, b, evals = cpu.run()
+        res[tag] = {"workload": w.name, "cycle_ms": gpu_ms, "logprob_evals": w.n_logprob_evals,
+                    "mcmc_ms": gp.timings_.get("mcmc_ms"),
+                    "cpu_port_cycle_ms": 1e3 * (a + b), "cpu_port_sample_ms": 1e3 * a, "cpu_port_ask_ms": 1e3 * b,
+                    "speedup": 1e3 * (a + b) / gpu_ms}
+    return res
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -197,14 +384,14 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     w = W.config3()
     m_local = len(w.candidates)
-    # weak scaling: the candidate set grows with the number of GPUs (10k per rank) and is sharded by
-    # bask_b200.distributed; the (tiny) MCMC is replicated with identical Philox streams, so the only
-    # collectives are the sweep's per-theta scalars and the final all-gather of acquisition values
+    # weak scaling: 128 walkers and 10k candidates per GPU, both sharded by bask_b200.distributed (walkers:
+    # every rank evaluates its slice of each half step's proposals and the log-probs are exchanged;
+    # candidates: contiguous blocks with per-theta scalar exchanges)
     cands = np.random.RandomState(21).uniform(size=(m_local * world, w.d)) if world > 1 else w.candidates
     gp = bask_b200.BayesGPR(kernel=construct_default_kernel(list(range(w.d))), normalize_y=True,
                             random_state=0, device=local)
     pg = dist.group.WORLD if world > 1 else None
-    Wk = w.n_walkers * world       # weak scaling: 128 walkers per GPU, sharded by bask_b200.distributed
+    Wk = w.n_walkers * world
     gp.fit(w.X, w.y, noise_vector=w.noise_vector, n_desired_samples=Wk, n_burnin=w.n_burnin,
            n_walkers_per_thread=Wk, progress=False, process_group=pg)
     e = gp._eng()
@@ -228,6 +415,7 @@ def run_b200(args):
         from bask_b200.distributed import DeviceBackend, ShardedSweep
         sweep = ShardedSweep(DeviceBackend(gp), dist.group.WORLD, keep_on_device=True)
     picks = np.random.RandomState(1).choice(len(gp.chain_), replace=False, size=S)
+    picks_dev = e.to_dev((picks % Wk).astype(np.int64), dtype=torch.int64)
     g32 = np.stack([bask_b200.acquisition.gumbel32_like_reference(K) for _ in range(S)])
     g32_dev = e.to_dev(g32, dtype=torch.float32)
     y_mean, y_std = float(gp.y_train_mean_), float(gp.y_train_std_)
@@ -237,14 +425,13 @@ def run_b200(args):
         with torch.cuda.stream(e.stream):
             flush.zero_()
         if world > 1:
-            from bask_b200.distributed import sharded_mcmc
-            chain_h, _pos_h, _acc = sharded_mcmc(e, gp.pos_, T, seed, 2.0, pg)
-            th = e.to_dev(chain_h[-1][picks % Wk])
+            from bask_b200.distributed import sharded_mcmc_dev
+            b = sharded_mcmc_dev(e, pos_dev, T, seed, 2.0, pg, buffers=bufs["mc"])
         else:
             b = e.mcmc(pos_dev, T, seed, buffers=bufs["mc"])
-            bufs["mc"] = b
-            with torch.cuda.stream(e.stream):
-                th = b["chain"][-1][torch.as_tensor(picks % Wk, device=e.device)].contiguous()
+        bufs["mc"] = b
+        with torch.cuda.stream(e.stream):
+            th = b["chain"][-1].index_select(0, picks_dev).contiguous()
         if sweep is not None:
             out = sweep.evaluate(Xc_dev, th, [(_lib.ACQ_MES, float("nan"))], {0: g32_dev})[0]
             return e.argmax(out.contiguous())
@@ -272,19 +459,24 @@ def run_b200(args):
     clocks = clk.summary(t_begin, t_end)
 
     # ---------------- end to end through the public API (host buffers in, host results out)
+    ask_ms = []
+
     def e2e_cycle(seed):
         with torch.cuda.stream(e.stream):
             flush.zero_()
         gp.sample(w.X, w.y, noise_vector=w.noise_vector, n_desired_samples=Wk, n_burnin=w.n_burnin,
                   n_walkers_per_thread=Wk, process_group=pg)
+        t0 = time.perf_counter()
         vals = bask_b200.evaluate_acquisitions(cands, gp, (mes,), n_samples=S, random_state=seed,
-                                               process_group=dist.group.WORLD if world > 1 else None,
-                                               **w.acq_kwargs)[0]
-        return int(np.argmax(vals))
+                                               process_group=pg, **w.acq_kwargs)[0]
+        best = int(np.argmax(vals))
+        ask_ms.append(1e3 * (time.perf_counter() - t0))
+        return best
 
     for i in range(args.warmup):
         e2e_cycle(i)
     barrier()
+    ask_ms.clear()
     t0 = time.perf_counter()
     for i in range(args.steps):
         e2e_cycle(10 + i)
@@ -296,77 +488,85 @@ def run_b200(args):
     # ---------------- roofline of the dominant kernel, timed alone on its launch stream
     nb = (w.n_walkers + 1) // 2
     th64 = e.to_dev(gp.chain_[:nb])
-    for _ in range(3):
-        e.logprob_dev(th64)
-    reps = 20
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e.sync()
-    k0.record(e.stream)
-    for _ in range(reps):
-        e.logprob_dev(th64)
-    k1.record(e.stream)
-    e.sync()
-    chol_ms = k0.elapsed_time(k1) / reps
+    chol_ms = _timed(e, lambda: e.logprob_dev(th64), 20, warm=3)
     peaks = json.load(open(os.path.join(REPO, "profiles", "fp64_peaks_r01.json")))
     peak_tf = float(peaks["dmma_tflops_w8"])
     try:    # DRAM bytes per launch of the factorisation kernel from the committed ncu --set full capture
-        traffic = json.load(open(os.path.join(REPO, "profiles", "ncu_traffic_r01.json")))["chol_lml_kernel"]
+        traffic = json.load(open(os.path.join(REPO, "profiles", "ncu_traffic_r02.json")))
     except Exception:
-        traffic = None
+        traffic = {}
     chol_tf = nb * flops_lml(w.n, w.d) / (chol_ms * 1e-3) / 1e12
+    # batched-theta LML throughput (BASELINE metric, first half): 1 024 thetas per call at n=500
+    th1k = e.to_dev(np.tile(gp.chain_[:128], (8, 1)) + 1e-3 * np.random.RandomState(5).randn(1024, w.d + 2))
+    lml_ms = _timed(e, lambda: e.logprob_dev(th1k), 5, warm=2)
     # sweep kernel
     th = e.to_dev(gp.chain_[picks])
     f = e.factorize(th)
-    Xc_dev = Xc_dev[:m_local].contiguous()
-    for _ in range(2):
-        e.predict(f, Xc_dev, noise_off=True, y_mean=y_mean, y_std=y_std)
-    e.sync()
-    k0.record(e.stream)
-    for _ in range(5):
-        e.predict(f, Xc_dev, noise_off=True, y_mean=y_mean, y_std=y_std)
-    k1.record(e.stream)
-    e.sync()
-    sweep_ms = k0.elapsed_time(k1) / 5
+    Xc_one = Xc_dev[:m_local].contiguous()
+    sweep_ms = _timed(e, lambda: e.predict(f, Xc_one, noise_off=True, y_mean=y_mean, y_std=y_std), 5, warm=2)
     sweep_tf = S * m_local * flops_sweep(w.n, w.d) / (sweep_ms * 1e-3) / 1e12
 
-    times = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=e.device)
+    times = torch.tensor([dev_ms, e2e_ms, float(np.mean(ask_ms))], dtype=torch.float64, device=e.device)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = [float(v) for v in times.cpu()]
+    dev_ms, e2e_ms, ask_lat = [float(v) for v in times.cpu()]
+
+    c5 = None
+    if not args.no_c5:
+        del f, flush
+        torch.cuda.empty_cache()
+        c5 = bench_c5(args, rank, world, local, pg)
 
     if rank == 0:
         evals = Wk * (1 + T)          # distinct log-posterior evaluations per cycle, all ranks together
         line = {"metric": METRIC, "value": evals / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": w.name, "n_obs": w.n, "dims": w.d, "walkers": Wk, "walkers_per_gpu": w.n_walkers, "mcmc_steps": T,
-                           "theta_samples": S, "candidates_per_gpu": m_local, "acquisition": w.acquisition,
+                "config": {"workload": w.name, "n_obs": w.n, "dims": w.d, "walkers": Wk, "walkers_per_gpu": w.n_walkers,
+                           "mcmc_steps": T, "theta_samples": S, "candidates_per_gpu": m_local,
+                           "acquisition": w.acquisition,
                            "l2": "256 MiB memset between steps (inside the timed region)",
-                           "multi_gpu": "weak scaling: 128 walkers and 10k candidates per GPU; walkers sharded with one all-gather of W/2 log-probs per half step, candidates sharded with per-theta scalar exchanges"},
+                           "multi_gpu": "weak scaling: 128 walkers and 10k candidates per GPU; walkers sharded (each "
+                                        "rank evaluates its slice of a half step's proposals, log-probs exchanged by "
+                                        "peer stores inside the CUDA graph), candidates sharded with per-theta scalar "
+                                        "exchanges"},
                 "clocks": clocks,
                 "e2e": {"value": evals / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                "lml_evals_per_s_batched": 1024 / (lml_ms * 1e-3),
+                "lml_batched_tflops": 1024 * flops_lml(w.n, w.d) / (lml_ms * 1e-3) / 1e12,
+                "ask_latency_ms": ask_lat,
                 "gpu_launches": int(launches),
-                "roofline": {"kernel": "scale_x + gram_kernel + chol_lml_kernel<8,2> (K1+K2: Gram, Cholesky, LML; 64 thetas, n=500)",
+                "roofline": {"kernel": "gram_kernel + chol_lml_kernel (K1+K2: Gram, Cholesky, LML; 64 thetas, n=500)",
                              "bound": "tensor", "achieved": chol_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                             "frac": chol_tf / peak_tf, "traffic": traffic,
-                             "traffic_note": "dram read+write bytes per launch from one ncu --set full capture (cold L2: ncu "
-                                             "flushes caches, in the pipeline the slabs are L2 hits); algorithmic bytes ~30 KB",
+                             "frac": chol_tf / peak_tf, "traffic": traffic.get("chol_lml_kernel"),
+                             "traffic_note": traffic.get("note"),
                              "peak_source": "measured FP64 DMMA.8x8x4 issue peak on this pool (profiles/fp64_peaks_r01.json; "
                                             "MEASURED_PEAKS.json has no FP64 entry; cuBLAS DGEMM 8192^3 = 35.5)",
                              "launch_ms": chol_ms},
-                "roofline_sweep": {"kernel": "sweep_kernel<4> (10 thetas x 10k candidates, n=500)", "bound": "tensor",
+                "roofline_sweep": {"kernel": "sweep_kernel (10 thetas x 10k candidates, n=500)", "bound": "tensor",
                                    "achieved": sweep_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                                   "frac": sweep_tf / peak_tf, "launch_ms": sweep_ms}}
+                                   "frac": sweep_tf / peak_tf, "launch_ms": sweep_ms,
+                                   "traffic": traffic.get("sweep_kernel")}}
+        if c5 is not None:
+            if "sweep_kernel_tflops" in c5:
+                c5["sweep_kernel_frac_of_dmma_peak"] = c5["sweep_kernel_tflops"] / peak_tf
+            line["c5"] = c5
         if world == 1 and not args.no_cpu_baseline:
-            cyc, detail = cpu_reference_cycle(w, lml_evals=48, sweep_thetas=1, sweep_cands=400)
+            cpu = CpuCycle(w)
+            a, b, ev = cpu.run(n_steps=3, n_cand=2500)
+            cyc = a * (w.n_logprob_evals / ev) + b * (len(w.candidates) / 2500)
             line["cpu_baseline"] = {
-                "value": w.n_logprob_evals / cyc, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                "sample": "48 log-posterior evals + 1 theta-setter + predict/MES over 400 candidates at n=500, "
-                          "extrapolated linearly to the full cycle (1536 evals + 10 x 10000 candidates)",
-                "cycle_s_extrapolated": cyc, "detail": detail}
+                "value": w.n_logprob_evals / cyc, "unit": UNIT, "cores": _threads_in_use(), "kind": "port",
+                "sample": "one reduced cycle of the CPU port: sample() with 128 walkers x 3 steps (%d log-posteriors, %.1f s) "
+                          "+ MES over 10 thetas x 2500 candidates (%.1f s), scaled to 1536 evaluations and 10000 "
+                          "candidates; `bench.py --impl reference` times complete cycles" % (ev, a, b),
+                "cycle_s_scaled": cyc}
+            line["small_configs"] = bench_small_configs(args)
         emit(line)
     if world > 1:
+        dist.barrier()
+        e.close_peers()
         dist.destroy_process_group()
 
 
@@ -377,6 +577,11 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the config-5 strong-scaling block")
+    ap.add_argument("--c5-candidates", type=int, default=100000)
+    ap.add_argument("--c5-reps", type=int, default=3)
+    ap.add_argument("--no-single-thread", action="store_true",
+                    help="reference arm: skip the extra OMP_NUM_THREADS=1 cycle")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

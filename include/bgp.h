@@ -229,6 +229,27 @@ int bgp_mcmc_accept(bgp_handle_t h, double* pos_dev, double* lp_dev, const doubl
  * NULL restores by-value seeds. */
 int bgp_mcmc_seed_source(bgp_handle_t h, const uint64_t* seed_dev);
 
+/* ---- multi-GPU walker sharding (one process per GPU, walkers split over the ranks) ----
+ * Replaces emcee's serial map over the walkers of a half step (bask/bayesgpr.py:510-530) across GPUs
+ * without NCCL and without the host: every rank evaluates its slice of the proposals and stores the
+ * log-probabilities straight into every peer's exchange block (cudaIpc mapping, NVLink P2P) followed by
+ * a release flag; the accept kernel acquires on the flags.  The whole run is one CUDA graph per rank and
+ * every rank ends with the same chain as bgp_mcmc_run on one GPU.
+ *   bgp_peer_export   allocates this rank's exchange block for up to max_walkers walkers and returns its
+ *                     cudaIpc handle (BGP_IPC_HANDLE_BYTES bytes; the host all-gathers them)
+ *   bgp_peer_connect  maps the blocks of all `world` ranks (ipc_handles: world x BGP_IPC_HANDLE_BYTES,
+ *                     rank order); world <= 8, one node
+ *   bgp_peer_close    unmaps them (before the process group is torn down)
+ *   bgp_peer_status   timed_out = 1 when an exchange ever waited longer than 10 s for a peer */
+#define BGP_IPC_HANDLE_BYTES 64
+int bgp_peer_export(bgp_handle_t h, int max_walkers, void* ipc_handle_out);
+int bgp_peer_connect(bgp_handle_t h, const void* ipc_handles, int rank, int world);
+int bgp_peer_close(bgp_handle_t h);
+int bgp_peer_status(bgp_handle_t h, int* timed_out);
+int bgp_mcmc_run_sharded(bgp_handle_t h, double* pos_dev, double* lp_dev, int W, int T, double a,
+                         uint64_t seed, double* chain_dev, double* lp_chain_dev, int32_t* accepted_dev,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -267,8 +267,84 @@ def g6():
     np.savez_compressed(os.path.join(HERE, "g6_branin_warp.npz"), **d)
 
 
+def _light_reference_gp(w, n_walkers, n_steps, seed=0):
+    """Reference BayesGPR fitted with a SHORT MCMC (the numbers pinned below are evaluated at fixed
+    thetas, so the chain only has to supply plausible hyper-parameters)."""
+    gp = BayesGPR(kernel=construct_default_kernel(list(range(w.d))), normalize_y=True, random_state=seed)
+    t0 = time.time()
+    gp.fit(w.X, w.y, noise_vector=w.noise_vector, n_desired_samples=n_walkers, n_burnin=n_steps - 1,
+           n_walkers_per_thread=n_walkers, progress=False)
+    print(f"  reference fit: {time.time() - t0:.1f}s, chain {gp.chain_.shape}")
+    return gp
+
+
+def g7():
+    """BASELINE config 5 (Ackley-20, n=2000, d=20, p=22): LML / log-posterior at 16 thetas, moments,
+    EI and MES at 4 thetas x 2000 candidates, and a 4-theta evaluate_acquisitions sweep (EI + MES)."""
+    print("G7: config 5 (Ackley-20 n=2000), 2000 candidates")
+    w = W.config5(m=2000)
+    gp = _light_reference_gp(w, 64, 3)
+    d = common(gp, w)
+    rs = np.random.RandomState(17)
+    base = gp.chain_[rs.choice(len(gp.chain_), 16, replace=False)].copy()
+    base[8:] += 0.15 * rs.randn(8, base.shape[1])      # a wider spread than a 3-step chain has
+    d["thetas"] = base
+    d["Xc"] = w.candidates
+    t0 = time.time()
+    d.update(per_theta_vectors(gp, d["thetas"], w.candidates, 4, w.mes_seed))
+    print(f"  per-theta vectors: {time.time() - t0:.1f}s")
+    gp.theta = d["theta_median"]
+    t0 = time.time()
+    d.update(sweep_vectors(gp, w.candidates, [ExpectedImprovement(), MaxValueSearch()], ["ei", "mes"],
+                           4, 1, w.mes_seed))
+    print(f"  sweep: {time.time() - t0:.1f}s")
+    d["alpha_median"] = gp.alpha_.copy()
+    d["L_median_diag"] = np.diag(gp.L_).copy()
+    for k in ("alpha_",):      # 4 x 2000 -- keep; drop nothing else: the file stays < 1 MB
+        pass
+    np.savez_compressed(os.path.join(HERE, "g7_ackley20_n2000.npz"), **d)
+
+
+def g8():
+    """BASELINE config 4 at the large sizes: reference LML / log-posterior at 16 thetas for n=2048 and
+    n=4096 (d=6, the C4 generator).  Only scalars are stored; the inputs are regenerated from
+    bench_workloads.config4 by the test."""
+    print("G8: config 4 LML at n=2048 / 4096")
+    d = {}
+    for n in (2048, 4096):
+        w, thetas = W.config4(n, 16)
+        gp = BayesGPR(kernel=construct_default_kernel(list(range(w.d))), normalize_y=True, random_state=0,
+                      optimizer=None)
+        # no MAP search, no MCMC: the skopt/sklearn fit with optimizer=None only installs the data
+        from skopt.learning import GaussianProcessRegressor as SkoptGPR
+        SkoptGPR.fit(gp, w.X, w.y)
+        priors = guess_priors(gp.kernel_)
+        t0 = time.time()
+        d[f"n{n}__thetas"] = thetas
+        d[f"n{n}__lml"] = np.array([gp.log_marginal_likelihood(t) for t in thetas])
+        d[f"n{n}__logprob"] = np.array([gp._log_prob_fn(t, priors=priors, warp_priors=None) for t in thetas])
+        d[f"n{n}__y_train"] = gp.y_train_
+        print(f"  n={n}: {time.time() - t0:.1f}s")
+    np.savez_compressed(os.path.join(HERE, "g8_lml_large_n.npz"), **d)
+
+
+def g9():
+    """Headline size, un-cut: the reference's evaluate_acquisitions over all 10 000 candidates of config 3
+    with S=10 thetas (MES + EI), theta picks random_state=1, Gumbel draws np.random.seed(2)."""
+    print("G9: config 3 full sweep (n=500, m=10000, S=10)")
+    w = W.config3()
+    gp = fitted_reference_gp(w, n_desired=128, n_burnin=1)
+    d = common(gp, w)
+    t0 = time.time()
+    d.update(sweep_vectors(gp, w.candidates, [MaxValueSearch(), ExpectedImprovement()],
+                           ["mes", "ei"], 10, 1, w.mes_seed))
+    print(f"  sweep: {time.time() - t0:.1f}s")
+    d = {k: v for k, v in d.items() if k not in ("X", "y_raw", "noise_vector")}   # regenerated by the test
+    np.savez_compressed(os.path.join(HERE, "g9_wavy6_full_sweep.npz"), **d)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["g1", "g2", "g3", "g4", "g5", "g6"]
+    which = sys.argv[1:] or ["g1", "g2", "g3", "g4", "g5", "g6", "g7", "g8", "g9"]
     for name in which:
         globals()[name]()
     for f in sorted(os.listdir(HERE)):
