@@ -213,6 +213,6 @@ def test_fixed_noise_level_becomes_a_sampled_hyperparameter():
     gp = bask.BayesGPR(kernel=bask.construct_default_kernel([0, 1]), normalize_y=True, random_state=0, noise=0.1)
     gp.fit(w.X, w.y, n_desired_samples=40, n_burnin=2, n_walkers_per_thread=20, progress=False)
     assert gp.noise_ == pytest.approx(0.1)
-    assert gp.chain_.shape[1] == 5 and len(gp.theta) == 5
+    assert gp.chain_.shape[1] == 4 and len(gp.theta) == 4   # log c, 2 length scales, log noise
     out = bask.evaluate_acquisitions(w.candidates, gp, [bask.ExpectedImprovement()], n_samples=4, random_state=0)
     assert out.shape == (1, 500) and np.all(np.isfinite(out))
