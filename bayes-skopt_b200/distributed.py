@@ -132,6 +132,19 @@ class ShardedSweep:
             dist.all_gather(parts, pad, group=self.group)
         return torch.cat([p[:, :sz] for p, sz in zip(parts, sizes)], dim=1)
 
+    def _same_on_all_ranks(self, g):
+        """The Gumbel variates of MaxValueSearch come from each process's GLOBAL numpy RNG (the reference's
+        convention, bask/acquisition.py:253-257), which the ranks have no reason to have seeded alike:
+        rank 0's draws are broadcast (S x K float32) so that every candidate block sees the same max-value
+        samples."""
+        dev = torch.device(getattr(self.b, "device", "cpu"))
+        t = g if torch.is_tensor(g) else torch.from_numpy(np.ascontiguousarray(g)).to(dev)
+        t = t.contiguous()
+        with self.b.stream_ctx():
+            dist.broadcast(t, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0,
+                           group=self.group)
+        return t if dev.type == "cuda" else t.numpy()
+
     def evaluate(self, X, thetas, acquisitions, gumbels=None):
         """See _evaluate; every tensor op and collective is issued on the backend's stream."""
         with self.b.stream_ctx():
@@ -197,7 +210,7 @@ class ShardedSweep:
                         dist.all_gather(parts, mine, group=self.group)
                     fit = torch.cat([p_[:n_] for p_, n_ in zip(parts, rows)], dim=0).contiguous()
                 kw["fit"] = fit
-                kw["gumbel"] = gumbels[j]
+                kw["gumbel"] = self._same_on_all_ranks(gumbels[j])
             vals, skipped = self.b.per_theta(kind, mu, sd, p0, **kw)
             with self.b.stream_ctx():
                 dist.all_reduce(skipped, op=dist.ReduceOp.MAX, group=self.group)
