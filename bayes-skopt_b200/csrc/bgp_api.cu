@@ -92,6 +92,7 @@ int bgp_create(bgp_handle_t* out, int device) {
   CUDA_TRY(bgp::prepare_mcmc());
   CUDA_TRY(bgp::prepare_acq());
   CUDA_TRY(bgp::prepare_sweep());
+  CUDA_TRY(bgp::prepare_small());
   CUDA_TRY(cudaMallocHost((void**)&h->seed_pinned, sizeof(uint64_t)));
   CUDA_TRY(h->mc_seed.ensure(sizeof(uint64_t)));
   *out = h;
@@ -253,6 +254,19 @@ static int ensure_logprob_workspace(bgp_handle_t h) {
 // K1 (Gram, all SMs) then K2 (factorisation, one CTA per theta), in waves of one slab per SM
 static int logprob_impl(bgp_handle_t h, const double* theta_dev, int batch, const double* lp_extra_dev,
                         double* lp_dev, double* lml_dev, int32_t* info_dev, cudaStream_t st) {
+  if (bgp::small_path_fits(h->n, h->d, h->host_prog.n_leaves)) {
+    // small n: one fused launch, the matrix never leaves shared memory
+    bgp::CholArgs A;
+    std::memset(&A, 0, sizeof(A));
+    A.X = h->X.as<double>(); A.y = h->y.as<double>(); A.alpha = h->alpha.as<double>();
+    A.theta = theta_dev; A.lp_extra = lp_extra_dev; A.lp = lp_dev; A.lml = lml_dev; A.info = info_dev;
+    A.prog = h->prog.as<DevProgram>(); A.fixed_ls = h->fixed_ls.as<double>();
+    A.priors = h->have_priors ? h->priors.as<bgp_prior_t>() : nullptr; A.n_priors = h->n_priors;
+    A.n = h->n; A.d = h->d; A.batch = batch;
+    A.dbg = h->dbg; A.dbg_tid = h->dbg_tid;
+    CUDA_TRY(bgp::launch_small(A, h->host_prog.n_leaves, h->sms, st));
+    return 0;
+  }
   if (ensure_logprob_workspace(h)) return -1;
   const int slots = slots_for(h), p = h->host_prog.n_theta;
   const size_t xt = bgp::gram_xt_doubles(h->n, h->d, h->host_prog.n_leaves);

@@ -31,33 +31,6 @@ struct CholSmem {
   int fail;
 };
 
-__device__ __forceinline__ double log_prior(const bgp_prior_t* pr, int n, const double* theta) {
-  double lp = 0.0;
-  for (int k = 0; k < n; ++k) {
-    const double x = theta[k];
-    const double* p = pr[k].p;
-    switch (pr[k].kind) {
-      case BGP_PRIOR_HALFNORMAL_SQRT:
-        lp += -0.22579135264472744 /* 0.5*log(2/pi) */ - log(p[0]) - exp(x) / (2.0 * p[0] * p[0]) +
-              0.5 * x - 0.6931471805599453;
-        break;
-      case BGP_PRIOR_ROUNDFLAT:
-        lp += -2.0 * (exp(-2.0 * p[2] * (x - log(p[0]))) + exp(2.0 * p[3] * (x - log(p[1])))) -
-              p[4] + x;
-        break;
-      case BGP_PRIOR_INVGAMMA:
-        lp += p[0] * log(p[1]) - lgamma(p[0]) - (p[0] + 1.0) * x - p[1] * exp(-x) + x;
-        break;
-      case BGP_PRIOR_NORMAL: {
-        double t = (x - p[0]) / p[1];
-        lp += -0.5 * t * t - log(p[1]) - 0.9189385332046727;
-      } break;
-      default: break;
-    }
-  }
-  return lp;
-}
-
 // ---- warp-level Cholesky of the 32x32 diagonal block + inverses of its 8x8 diagonal blocks --
 // Right-looking over 8-column blocks with the block held in DMMA accumulator layout (lane (r,q)
 // owns [8t+r][8u+2q..2q+1] of sub-tile (t,u)):

@@ -188,6 +188,35 @@ __device__ __forceinline__ double bgp_warp_coord(const DevProgram& P, const doub
   return bgp_beta_cdf(x, exp(theta[P.warp_off + kk]), exp(theta[P.warp_off + P.n_warp + kk]));
 }
 
+// ------------------------------------------------------------------------------ priors
+// typed log-priors of a theta row (bask/utils.py:68-124, bask/priors.py:7-57), summed in table order
+__device__ __forceinline__ double log_prior(const bgp_prior_t* pr, int n, const double* theta) {
+  double lp = 0.0;
+  for (int k = 0; k < n; ++k) {
+    const double x = theta[k];
+    const double* p = pr[k].p;
+    switch (pr[k].kind) {
+      case BGP_PRIOR_HALFNORMAL_SQRT:
+        lp += -0.22579135264472744 /* 0.5*log(2/pi) */ - log(p[0]) - exp(x) / (2.0 * p[0] * p[0]) +
+              0.5 * x - 0.6931471805599453;
+        break;
+      case BGP_PRIOR_ROUNDFLAT:
+        lp += -2.0 * (exp(-2.0 * p[2] * (x - log(p[0]))) + exp(2.0 * p[3] * (x - log(p[1])))) -
+              p[4] + x;
+        break;
+      case BGP_PRIOR_INVGAMMA:
+        lp += p[0] * log(p[1]) - lgamma(p[0]) - (p[0] + 1.0) * x - p[1] * exp(-x) + x;
+        break;
+      case BGP_PRIOR_NORMAL: {
+        double t = (x - p[0]) / p[1];
+        lp += -0.5 * t * t - log(p[1]) - 0.9189385332046727;
+      } break;
+      default: break;
+    }
+  }
+  return lp;
+}
+
 // ------------------------------------------------------------------------------- DMMA
 // D(8x8) += A(8x4, row) * B(4x8, col).  Lane l holds A[l>>2][l&3], B[l&3][l>>2],
 // D[l>>2][2(l&3)], D[l>>2][2(l&3)+1].  SASS: DMMA.8x8x4 (tcgen05 has no f64 kind).

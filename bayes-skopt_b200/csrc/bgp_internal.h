@@ -35,6 +35,10 @@ cudaError_t prepare_chol(int n);
 cudaError_t prepare_mcmc();   // one-time opt-ins to large dynamic shared memory (outside capture)
 cudaError_t prepare_acq();
 cudaError_t launch_chol(const CholArgs& A, int grid, int sms, cudaStream_t stream);
+// small n: Gram + factorisation + LML fused, the matrix resident in shared memory (bgp_small.cu)
+cudaError_t prepare_small();
+bool small_path_fits(int n, int d, int n_leaves);
+cudaError_t launch_small(const CholArgs& A, int n_leaves, int sms, cudaStream_t stream);
 
 struct GramArgs {
   const double* X;       // n x d

@@ -143,3 +143,34 @@ def test_kernel_zoo_on_device(g4):
                                  y_std=float(g4[f"{name}__y_std"][0]))
         np.testing.assert_allclose(e.to_host(mu), g4[f"{name}__mu"], rtol=1e-8, atol=1e-9, err_msg=name)
         np.testing.assert_allclose(e.to_host(sd), g4[f"{name}__std"], rtol=1e-6, atol=1e-8, err_msg=name)
+
+
+# the fused shared-memory path (bgp_small.cu) covers n <= ~224; 7/8/9, 16/17: tile boundaries of its 8-wide
+# blocks; 96/97: 4- vs 8-warp variant; 224: the largest n whose tiles fit; 225: first n on the blocked path
+@pytest.mark.parametrize("n,d", [(3, 1), (7, 2), (8, 2), (9, 2), (16, 3), (17, 3), (20, 2), (96, 6), (97, 6),
+                                 (100, 6), (160, 20), (224, 6), (225, 6)])
+def test_small_fused_path_matches_oracle_and_blocked_path(n, d, monkeypatch):
+    r = np.random.RandomState(1000 + n)
+    X = r.uniform(size=(n, d))
+    y = np.sin(3 * X.sum(1)) + 0.1 * r.randn(n)
+    y = (y - y.mean()) / y.std()
+    alpha = 1e-10 + 0.01 * r.uniform(size=n)
+    e = make_engine(X, y, alpha, d)
+    spec = spec_for(d)
+    priors = G.guess_priors(spec)
+    B = 333                                            # more thetas than resident CTAs at the larger n
+    thetas = W.centre_theta(d) + 0.2 * r.randn(B, d + 2)
+    thetas[5, -1] = -800.0                            # zero noise; with duplicate-free X still PD (alpha > 0)
+    lp, lml, info = e.logprob(thetas)
+    monkeypatch.setenv("BGP_NO_SMALL", "1")
+    lp_b, lml_b, info_b = e.logprob(thetas)
+    monkeypatch.delenv("BGP_NO_SMALL")
+    np.testing.assert_array_equal(info, info_b)
+    np.testing.assert_allclose(lml, lml_b, rtol=1e-11)
+    np.testing.assert_allclose(lp, lp_b, rtol=1e-11)
+    pick = r.choice(B, size=6, replace=False)
+    ref_lml = [G.log_marginal_likelihood(spec, t, X, y, alpha) for t in thetas[pick]]
+    ref_lp = [G.log_prob(spec, t, X, y, alpha, priors) for t in thetas[pick]]
+    np.testing.assert_allclose(lml[pick], ref_lml, rtol=1e-8)
+    np.testing.assert_allclose(lp[pick], ref_lp, rtol=1e-8)
+
