@@ -254,6 +254,20 @@ class Engine:
         self.launches += 2 if what == _lib.EXTRACT_KINV else 1
         return out
 
+    def lml_gradient(self, theta_row):
+        """(LML, dLML/dtheta, info) at one theta row: factorise, extract alpha_ and K_inv_, then the
+        analytic-gradient kernel (sklearn:_gpr.py:583-651).  The gradient covers the kernel's own
+        hyper-parameters (the first ``p_kernel`` entries of the row)."""
+        f = self.factorize(np.atleast_2d(theta_row))
+        alpha = self.extract(f, 0, _lib.EXTRACT_ALPHA)
+        kinv = self.extract(f, 0, _lib.EXTRACT_KINV)
+        grad = self.empty(max(self.p_kernel, 1))
+        check(self.lib.bgp_lml_gradient(self.h, _ptr(f.thetas), _ptr(alpha), _ptr(kinv), _ptr(grad), self._st),
+              "bgp_lml_gradient")
+        self.launches += 3
+        self.stream.synchronize()
+        return float(f.lml.cpu().numpy()[0]), grad.cpu().numpy()[: self.p_kernel], int(f.info.cpu().numpy()[0])
+
     # ------------------------------------------------------------------ K4
     def predict(self, factor, Xc_dev, thetas_dev=None, noise_off=True, y_mean=0.0, y_std=1.0,
                 zextra=None, want_v=False):

@@ -42,6 +42,7 @@ _SIGNATURES = {
     "bgp_factor_slab_doubles": [_P],
     "bgp_factorize_batched": [_P, _P, C.c_int, _P, _P, _P, _P, _P],
     "bgp_factor_extract": [_P, _P, _P, C.c_int, _P, _P],
+    "bgp_lml_gradient": [_P, _P, _P, _P, _P, _P],
     "bgp_predict_batched": [_P, _P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_double, C.c_double,
                             _P, _P, _P, C.c_int, _P, _P, C.c_int64, _P],
     "bgp_acq_sweep": [_P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_double, _P, C.c_int, _P, _P, _P, _P, _P],

@@ -280,8 +280,9 @@ class BayesGPR:
 
     # ------------------------------------------------------------------ log-probabilities
     def log_marginal_likelihood(self, theta=None, eval_gradient=False, clone_kernel=True):
-        """LML of theta on device (sklearn:_gpr.py:541-656).  The gradient, used only by the MAP
-        start of ``fit``, is a central difference over one batched launch of 2p+1 thetas."""
+        """LML of theta on device (sklearn:_gpr.py:541-656); with ``eval_gradient`` also its analytic
+        gradient 1/2 tr((alpha alpha^T - K^-1) dK/dtheta) (``bgp_lml_gradient``), which drives the
+        L-BFGS-B MAP start of ``fit``."""
         if theta is None:
             if eval_gradient:
                 raise ValueError("Gradient can only be evaluated for theta!=None")
@@ -293,18 +294,10 @@ class BayesGPR:
         if not eval_gradient:
             _, lml, _ = e.logprob(self._theta_for_device(theta)[None, :])
             return float(lml[0])
-        h = 1e-5
-        p = len(theta)
-        batch = np.repeat(theta[None, :], 2 * p + 1, axis=0)
-        for k in range(p):
-            batch[1 + 2 * k, k] += h
-            batch[2 + 2 * k, k] -= h
-        _, lml, _ = e.logprob(self._theta_for_device(batch))
-        if not np.isfinite(lml[0]):
+        lml, grad, info = e.lml_gradient(self._theta_for_device(theta))
+        if info != 0 or not np.isfinite(lml):
             return -np.inf, np.zeros_like(theta)
-        grad = (lml[1::2] - lml[2::2]) / (2 * h)
-        grad[~np.isfinite(grad)] = 0.0
-        return float(lml[0]), grad
+        return lml, grad
 
     def _prior_table(self, priors, warp_priors, n_kernel):
         """(device prior table, host part) over a full theta row: the kernel's priors followed,
@@ -576,11 +569,11 @@ class BayesGPR:
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")
                 self.kernel_._check_bounds_params()
-            self.log_marginal_likelihood_value_ = -np.min(lml_values)
+            map_lml = -np.min(lml_values)
         else:
-            self.log_marginal_likelihood_value_ = self.log_marginal_likelihood(self.kernel_.theta,
-                                                                              clone_kernel=False)
+            map_lml = self.log_marginal_likelihood(self.kernel_.theta, clone_kernel=False)
         self._refactor()
+        self.log_marginal_likelihood_value_ = map_lml      # (the refactorisation clears the cached value)
         self.noise_ = None
         if self.noise:
             if isinstance(self.kernel_, WhiteKernel):

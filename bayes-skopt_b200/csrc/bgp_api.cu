@@ -356,6 +356,29 @@ int bgp_factor_extract(bgp_handle_t h, const double* slab_dev, const double* z_d
   return 0;
 }
 
+int bgp_lml_gradient(bgp_handle_t h, const double* theta_dev, const double* alpha_dev, const double* kinv_dev,
+                     double* grad_dev, void* stream) {
+  CHECK_H(h);
+  if (ready(h)) return -1;
+  if (!theta_dev || !alpha_dev || !kinv_dev || !grad_dev) return fail("bad gradient arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const DevProgram& P = h->host_prog;
+  const int p_kernel = P.n_warp ? P.warp_off : P.n_theta;
+  if (p_kernel <= 0) return 0;
+  const size_t xt = bgp::gram_xt_doubles(h->n, h->d, P.n_leaves);
+  CUDA_TRY(h->xt_scratch.ensure(sizeof(double) * xt * (size_t)slots_for(h)));
+  CUDA_TRY(h->extract_scratch.ensure(sizeof(double) * ((size_t)h->n * h->n + bgp::grad_partial_doubles(h->n, p_kernel))));
+  bgp::GramArgs Gm{h->X.as<double>(), h->alpha.as<double>(), theta_dev, nullptr, h->xt_scratch.as<double>(),
+                   (long long)xt, h->prog.as<DevProgram>(), h->fixed_ls.as<double>(), h->n, h->d, 1, 0};
+  CUDA_TRY(bgp::launch_scale_x(Gm, st));
+  // the partial sums live behind the n x n region that bgp_factor_extract(K_INV) uses as its own scratch
+  bgp::GradArgs A{h->xt_scratch.as<double>(), alpha_dev, kinv_dev, h->extract_scratch.as<double>() + (size_t)h->n * h->n,
+                  grad_dev, h->prog.as<DevProgram>(), h->n, h->d, P.n_leaves, p_kernel};
+  CUDA_TRY(bgp::launch_lml_grad(A, st));
+  return 0;
+}
+
 int bgp_predict_batched(bgp_handle_t h, const double* theta_dev, int S, const double* slabs_dev,
                         const double* z_dev, const double* Xc_dev, int m, int noise_off, double y_mean,
                         double y_std, double* mu_dev, double* sd_dev, const double* zextra_dev, int R,

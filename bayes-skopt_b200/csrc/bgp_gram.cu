@@ -159,11 +159,17 @@ size_t gram_xt_doubles(int n, int d, int n_leaves) {
   return (size_t)(n_leaves > 0 ? n_leaves : 1) * d * gram_nx(n) + 32;   // + resolved op constants
 }
 
-cudaError_t launch_gram(const GramArgs& A, cudaStream_t stream) {
-  const int P = (A.n + 31) / 32;
+cudaError_t launch_scale_x(const GramArgs& A, cudaStream_t stream) {
   const int per_theta = (int)((gram_xt_doubles(A.n, A.d, 1) * 4 + 255) / 256);
   dim3 gs(per_theta < 1 ? 1 : (per_theta > 32 ? 32 : per_theta), A.batch);
   scale_x_kernel<<<gs, 256, 0, stream>>>(A);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gram(const GramArgs& A, cudaStream_t stream) {
+  const int P = (A.n + 31) / 32;
+  cudaError_t e0 = launch_scale_x(A, stream);
+  if (e0 != cudaSuccess) return e0;
   int chunks = 0;
   for (int k = 0; k < P; ++k) chunks += gram_chunks(A.n, k);
   dim3 gg(chunks, A.batch);

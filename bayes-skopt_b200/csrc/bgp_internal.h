@@ -53,6 +53,20 @@ struct GramArgs {
 };
 size_t gram_xt_doubles(int n, int d, int n_leaves);
 cudaError_t launch_gram(const GramArgs& A, cudaStream_t stream);
+cudaError_t launch_scale_x(const GramArgs& A, cudaStream_t stream);   // the first half of launch_gram
+
+// analytic LML gradient (bgp_grad.cu)
+struct GradArgs {
+  const double* xt;         // scaled transposed inputs + resolved op constants of ONE theta (launch_scale_x)
+  const double* alpha_vec;  // alpha_ = K^-1 y (n)
+  const double* kinv;       // K_inv_ (n x n)
+  double* partial;          // grad_partial_doubles(n, p_kernel) workspace
+  double* grad;             // p_kernel outputs
+  const DevProgram* prog;
+  int n, d, n_leaves, p_kernel;
+};
+size_t grad_partial_doubles(int n, int p);
+cudaError_t launch_lml_grad(const GradArgs& A, cudaStream_t stream);
 cudaError_t launch_warp_points(const double* X, int npts, int d, const double* theta, int S, const DevProgram* prog,
                                double* out, cudaStream_t stream);
 

@@ -121,6 +121,15 @@ enum bgp_extract_what {
 int bgp_factor_extract(bgp_handle_t h, const double* slab_dev, const double* z_dev, int what,
                        double* out_dev, void* stream);
 
+/* ---- analytic LML gradient (MAP start of fit) ---------------------------------------
+ * grad[k] = 1/2 tr((alpha alpha^T - K^-1) dK/dtheta_k) over the kernel's own log hyper-parameters
+ * (input-warp entries of a theta row are not differentiated); replaces
+ * log_marginal_likelihood(theta, eval_gradient=True) of sklearn:_gpr.py:619-651 as driven by the
+ * L-BFGS-B search of the skopt fit (bask/bayesgpr.py:607).  alpha_dev (n) and kinv_dev (n x n) are
+ * bgp_factor_extract(BGP_EXTRACT_ALPHA / BGP_EXTRACT_KINV) of the factorisation at theta_dev (one row). */
+int bgp_lml_gradient(bgp_handle_t h, const double* theta_dev, const double* alpha_dev,
+                     const double* kinv_dev, double* grad_dev, void* stream);
+
 /* ---- K4: candidate sweep ------------------------------------------------------------
  * For S thetas and m candidates: mu[s,i] = y_std * k*(x_i)^T K^-1 y + y_mean and
  * sd[s,i] = sqrt(max(0, k(x_i,x_i) - k*^T K^-1 k*) * y_std^2); replaces gpr.predict

@@ -224,6 +224,80 @@ def kernel_diag(spec, X):
     return np.ones(m)
 
 
+# ------------------------------------------------------- kernel gradient (MAP start of fit)
+def _stationary_gradient(tag, spec, X):
+    """d k(X, X) / d log(length scale): sklearn kernels.py:1571-1587 (RBF) and :1744-1786 (Matern).
+    D[i, j, k] = ((x_ik - x_jk) / l_k)^2; an isotropic length scale gets the sum over k."""
+    ls = spec[1]
+    fixed = spec[-1]
+    n = X.shape[0]
+    if fixed:
+        return np.zeros((n, n, 0))
+    iso = np.ndim(ls) == 0
+    D = (X[:, None, :] - X[None, :, :]) ** 2 / (np.asarray(ls, dtype=np.float64) ** 2)
+    r2 = D.sum(-1)
+    if tag == "rbf" or spec[2] == np.inf:
+        K = np.exp(-0.5 * r2)
+        G = D * K[..., None]
+    else:
+        nu = spec[2]
+        if nu == 0.5:
+            K = np.exp(-np.sqrt(r2))
+            with np.errstate(divide="ignore", invalid="ignore"):
+                G = K[..., None] * D / np.sqrt(r2)[..., None]
+            G[~np.isfinite(G)] = 0
+        elif nu == 1.5:
+            G = 3 * D * np.exp(-np.sqrt(3 * r2))[..., None]
+        elif nu == 2.5:
+            t = np.sqrt(5 * r2)[..., None]
+            G = 5.0 / 3.0 * D * (t + 1) * np.exp(-t)
+        else:
+            raise NotImplementedError("general-nu Matern (Bessel kv) is outside the path")
+    return G.sum(-1, keepdims=True) if iso else G
+
+
+def kernel_gradient(spec, X):
+    """(K, dK/dtheta) with dK of shape (n, n, n_theta(spec)), theta in log space, sklearn order --
+    Sum :856-873, Product :957-973, Exponentiation :1104-1118, ConstantKernel :1284-1296,
+    WhiteKernel :1407-1419 of sklearn/gaussian_process/kernels.py."""
+    tag = spec[0]
+    X = np.atleast_2d(X)
+    n = X.shape[0]
+    if tag == "sum":
+        K1, G1 = kernel_gradient(spec[1], X)
+        K2, G2 = kernel_gradient(spec[2], X)
+        return K1 + K2, np.dstack((G1, G2))
+    if tag == "product":
+        K1, G1 = kernel_gradient(spec[1], X)
+        K2, G2 = kernel_gradient(spec[2], X)
+        return K1 * K2, np.dstack((G1 * K2[:, :, None], G2 * K1[:, :, None]))
+    if tag == "exp":
+        K, G = kernel_gradient(spec[1], X)
+        return K ** spec[2], G * (spec[2] * K[:, :, None] ** (spec[2] - 1))
+    K = kernel_matrix(spec, X)
+    if tag == "const":
+        return K, (np.zeros((n, n, 0)) if spec[2] else np.full((n, n, 1), spec[1], dtype=np.float64))
+    if tag == "white":
+        return K, (np.zeros((n, n, 0)) if spec[2] else (spec[1] * np.eye(n))[:, :, None])
+    return K, _stationary_gradient(tag, spec, X)
+
+
+def lml_gradient(spec, theta, X, y, alpha):
+    """(LML, dLML/dtheta): sklearn _gpr.py:583-651 --
+    0.5 * einsum("ijl,jik->kl", alpha alpha^T - K^-1, dK) for the single-output case."""
+    K, dK = kernel_gradient(with_theta(spec, theta), X)
+    K = K.copy()
+    K[np.diag_indices_from(K)] += alpha
+    try:
+        L = cholesky(K, lower=True, check_finite=False)
+    except np.linalg.LinAlgError:
+        return -np.inf, np.zeros(len(theta))
+    a = cho_solve((L, True), y, check_finite=False)
+    lml = float(-0.5 * np.dot(y, a) - np.log(np.diag(L)).sum() - K.shape[0] / 2 * LOG_2PI)
+    inner = np.outer(a, a) - cho_solve((L, True), np.eye(K.shape[0]), check_finite=False)
+    return lml, 0.5 * np.einsum("ij,jik->k", inner, dK)
+
+
 # ------------------------------------------------------------------------ priors
 class HalfNormalOnSqrt:
     """log-density of theta = log v when sqrt(v) ~ half-normal(scale): the prior

@@ -343,8 +343,54 @@ def g9():
     np.savez_compressed(os.path.join(HERE, "g9_wavy6_full_sweep.npz"), **d)
 
 
+def g10():
+    """LML gradients and the MAP start: sklearn's
+    log_marginal_likelihood(theta, eval_gradient=True) -- what the L-BFGS-B search of the skopt fit
+    drives (bask/bayesgpr.py:607 -> sklearn _gpr.py:299-344, 583-651) -- at the 16 thetas of g1/g2/g3 and at
+    the kernel-zoo thetas of g4, plus the MAP point of that search (theta with the noise level in the White
+    slot, noise_, LML) on the g1/g2/g3 data."""
+    print("G10: LML gradients + MAP points")
+    from skopt.learning import GaussianProcessRegressor as SkoptGPR
+    d = {}
+    for tag, name, dim in (("g1", "g1_branin_n20.npz", 2), ("g2", "g2_hartmann6_n100.npz", 6),
+                           ("g3", "g3_wavy6_n500.npz", 6)):
+        g = np.load(os.path.join(HERE, name))
+        t0 = time.time()
+        gp = BayesGPR(kernel=construct_default_kernel(list(range(dim))), normalize_y=True, random_state=0,
+                      optimizer=None, alpha=g["alpha_vec"])
+        SkoptGPR.fit(gp, g["X"], g["y_raw"])
+        assert np.allclose(gp.y_train_, g["y_train"], rtol=0, atol=1e-13)
+        vals = [gp.log_marginal_likelihood(t, eval_gradient=True) for t in g["thetas"]]
+        d[f"{tag}__lml"] = np.array([v[0] for v in vals])
+        d[f"{tag}__grad"] = np.array([v[1] for v in vals])
+        gm = BayesGPR(kernel=construct_default_kernel(list(range(dim))), normalize_y=True, random_state=0,
+                      alpha=g["alpha_vec"])
+        SkoptGPR.fit(gm, g["X"], g["y_raw"])
+        th = gm.kernel_.theta.copy()
+        th[np.isinf(th)] = np.log(gm.noise_)
+        d[f"{tag}__map_theta"] = th
+        d[f"{tag}__map_noise"] = np.atleast_1d(gm.noise_)
+        d[f"{tag}__map_lml"] = np.atleast_1d(gm.log_marginal_likelihood_value_)
+        print(f"  {tag}: {time.time() - t0:.1f}s  MAP theta {np.round(th, 3)}")
+    g4d = np.load(os.path.join(HERE, "g4_kernel_zoo.npz"))
+    zoo = {
+        "const_plus_matern15_iso": ConstantKernel(1.0) + Matern(0.4, nu=1.5),
+        "const_times_rbf_ard": ConstantKernel(1.5) * RBF([0.3, 0.5, 0.7]),
+        "matern05_ard_fixedconst": ConstantKernel(2.0, "fixed") * Matern([0.5, 0.4, 0.3], nu=0.5),
+        "exp2_of_sum": Exponentiation(ConstantKernel(0.5) * Matern(0.6, nu=2.5) + RBF([1.0, 1.0, 1.0]), 2.0),
+        "matern_inf_iso": ConstantKernel(1.0) * Matern(0.5, nu=np.inf),
+        "product_of_stationary": ConstantKernel(1.0) * RBF(0.8) * Matern([0.9, 0.8, 0.7], nu=2.5),
+    }
+    for name, kern in zoo.items():
+        gp = BayesGPR(kernel=kern, normalize_y=True, random_state=3, optimizer=None)
+        SkoptGPR.fit(gp, g4d["X"], g4d["y_raw"])
+        vals = [gp.log_marginal_likelihood(t, eval_gradient=True) for t in g4d[f"{name}__thetas"]]
+        d[f"zoo_{name}__grad"] = np.array([v[1] for v in vals])
+    np.savez_compressed(os.path.join(HERE, "g10_lml_gradients.npz"), **d)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["g1", "g2", "g3", "g4", "g5", "g6", "g7", "g8", "g9"]
+    which = sys.argv[1:] or ["g1", "g2", "g3", "g4", "g5", "g6", "g7", "g8", "g9", "g10"]
     for name in which:
         globals()[name]()
     for f in sorted(os.listdir(HERE)):

@@ -216,3 +216,66 @@ def test_fixed_noise_level_becomes_a_sampled_hyperparameter():
     assert gp.chain_.shape[1] == 4 and len(gp.theta) == 4   # log c, 2 length scales, log noise
     out = bask.evaluate_acquisitions(w.candidates, gp, [bask.ExpectedImprovement()], n_samples=4, random_state=0)
     assert out.shape == (1, 500) and np.all(np.isfinite(out))
+
+
+# ---------------------------------------------------------------- N3 / A16: LML gradient and the MAP start
+@pytest.fixture(scope="module")
+def g10():
+    return load_golden("g10_lml_gradients.npz")
+
+
+@pytest.mark.parametrize("tag,name,d", [("g1", "g1_branin_n20.npz", 2), ("g2", "g2_hartmann6_n100.npz", 6),
+                                        ("g3", "g3_wavy6_n500.npz", 6)])
+def test_lml_gradient_matches_reference(tag, name, d, g10):
+    """log_marginal_likelihood(theta, eval_gradient=True) of the reference (sklearn _gpr.py:583-651) at 16 thetas."""
+    g = load_golden(name)
+    e = _engine(g["X"], g["y_train"], g["alpha_vec"], d)
+    for t, lml_ref, grad_ref in zip(g["thetas"], g10[f"{tag}__lml"], g10[f"{tag}__grad"]):
+        lml, grad, info = e.lml_gradient(t)
+        assert info == 0
+        np.testing.assert_allclose(lml, lml_ref, rtol=RTOL)
+        np.testing.assert_allclose(grad, grad_ref, rtol=RTOL, atol=RTOL * np.abs(grad_ref).max())
+
+
+def test_lml_gradient_kernel_zoo(g10):
+    """dual-number evaluation of the covariance program: Sum / Product / Exponentiation, Matern 1/2, 3/2, 5/2, inf,
+    RBF, isotropic / ARD / fixed leaves (g4 data)."""
+    import bask_b200  # noqa: F401
+    from bask_b200._engine import Engine
+    from sklearn.gaussian_process.kernels import RBF, ConstantKernel, Exponentiation, Matern, WhiteKernel
+    g4 = load_golden("g4_kernel_zoo.npz")
+    zoo = {
+        "const_plus_matern15_iso": ConstantKernel(1.0) + Matern(0.4, nu=1.5),
+        "const_times_rbf_ard": ConstantKernel(1.5) * RBF([0.3, 0.5, 0.7]),
+        "matern05_ard_fixedconst": ConstantKernel(2.0, "fixed") * Matern([0.5, 0.4, 0.3], nu=0.5),
+        "exp2_of_sum": Exponentiation(ConstantKernel(0.5) * Matern(0.6, nu=2.5) + RBF([1.0, 1.0, 1.0]), 2.0),
+        "matern_inf_iso": ConstantKernel(1.0) * Matern(0.5, nu=np.inf),
+        "product_of_stationary": ConstantKernel(1.0) * RBF(0.8) * Matern([0.9, 0.8, 0.7], nu=2.5),
+    }
+    for name, base in zoo.items():
+        e = Engine()
+        e.set_kernel(base + WhiteKernel())
+        e.set_data(g4["X"], g4[f"{name}__y_train"], 1e-10)
+        for t, lml_ref, grad_ref in zip(g4[f"{name}__thetas"], g4[f"{name}__lml"], g10[f"zoo_{name}__grad"]):
+            lml, grad, info = e.lml_gradient(t)
+            assert info == 0
+            np.testing.assert_allclose(lml, lml_ref, rtol=RTOL, err_msg=name)
+            np.testing.assert_allclose(grad, grad_ref, rtol=RTOL, atol=RTOL * np.abs(grad_ref).max(), err_msg=name)
+
+
+@pytest.mark.parametrize("tag,name,d", [("g1", "g1_branin_n20.npz", 2), ("g2", "g2_hartmann6_n100.npz", 6),
+                                        ("g3", "g3_wavy6_n500.npz", 6)])
+def test_map_start_matches_reference(tag, name, d, g10):
+    """A16: the MAP point of the L-BFGS-B search that precedes the MCMC (skopt fit: kernel_.theta, noise_, LML).
+    Same optimiser (scipy L-BFGS-B), same start, gradient and LML equal to 1e-8 -> the same optimum up to
+    the optimiser's own stopping tolerance."""
+    import bask_b200 as bask
+    g = load_golden(name)
+    gp = bask.BayesGPR(kernel=bask.construct_default_kernel(list(range(d))), normalize_y=True, random_state=0,
+                       alpha=g["alpha_vec"])
+    gp._fit_map(g["X"], g["y_raw"])
+    th = gp.theta
+    th[np.isinf(th)] = np.log(gp.noise_)
+    np.testing.assert_allclose(gp.log_marginal_likelihood_value_, g10[f"{tag}__map_lml"][0], rtol=1e-6)
+    np.testing.assert_allclose(th, g10[f"{tag}__map_theta"], atol=2e-3)
+    np.testing.assert_allclose(gp.noise_, g10[f"{tag}__map_noise"][0], rtol=5e-3)

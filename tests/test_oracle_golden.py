@@ -7,6 +7,7 @@ import pytest
 import bench_workloads as W
 from oracle import acq_oracle as A
 from oracle import gp_oracle as G
+from conftest import load_golden
 
 RTOL = 1e-10
 
@@ -167,3 +168,28 @@ def test_warped_log_prob(g6):
         np.testing.assert_allclose(std, g["std"][s], rtol=1e-8, atol=1e-12)
     np.testing.assert_allclose(G.warp_inputs(g["X"], g["warp_alphas"], g["warp_betas"]), g["X_train_warped"],
                                rtol=1e-12)
+
+
+def test_lml_gradient_restatement():
+    """N3: oracle gradient (sklearn _gpr.py:619-651 + kernel gradients) against the reference's
+    log_marginal_likelihood(eval_gradient=True) on g1/g2 data and on the kernel zoo."""
+    g10 = load_golden("g10_lml_gradients.npz")
+    for tag, name, d in (("g1", "g1_branin_n20.npz", 2), ("g2", "g2_hartmann6_n100.npz", 6)):
+        g = load_golden(name)
+        spec = default_spec(d)
+        for t, lml_ref, grad_ref in list(zip(g["thetas"], g10[f"{tag}__lml"], g10[f"{tag}__grad"]))[:6]:
+            lml, grad = G.lml_gradient(spec, t, g["X"], g["y_train"], g["alpha_vec"])
+            np.testing.assert_allclose(lml, lml_ref, rtol=RTOL)
+            np.testing.assert_allclose(grad, grad_ref, rtol=1e-9, atol=1e-9 * np.abs(grad_ref).max())
+    g4 = load_golden("g4_kernel_zoo.npz")
+    zoo = {
+        "const_plus_matern15_iso": ("sum", ("const", 1.0, False), ("matern", 0.4, 1.5, False)),
+        "matern05_ard_fixedconst": ("product", ("const", 2.0, True), ("matern", np.array([0.5, 0.4, 0.3]), 0.5, False)),
+        "exp2_of_sum": ("exp", ("sum", ("product", ("const", 0.5, False), ("matern", 0.6, 2.5, False)),
+                                ("rbf", np.ones(3), False)), 2.0),
+    }
+    for name, base in zoo.items():
+        spec = ("sum", base, ("white", 1.0, False))
+        for t, grad_ref in zip(g4[f"{name}__thetas"], g10[f"zoo_{name}__grad"]):
+            _, grad = G.lml_gradient(spec, t, g4["X"], g4[f"{name}__y_train"], 1e-10 * np.ones(len(g4["X"])))
+            np.testing.assert_allclose(grad, grad_ref, rtol=1e-9, atol=1e-9 * np.abs(grad_ref).max(), err_msg=name)
