@@ -10,8 +10,10 @@ from .acquisition import (LCB, PVRS, Expectation, ExpectedImprovement, MaxValueS
                           ThompsonSampling, TopTwoEI, VarianceReduction, evaluate_acquisitions)
 from .bayesgpr import BayesGPR  # noqa: F401
 from .optimizer import Optimizer, r2_sequence, sb_sequence  # noqa: F401
+from .searchcv import BayesSearchCV  # noqa: F401
 from .utils import construct_default_kernel, geometric_median, guess_priors  # noqa: F401
 
 __all__ = ["BayesGPR", "Optimizer", "guess_priors", "construct_default_kernel", "geometric_median",
            "evaluate_acquisitions", "ExpectedImprovement", "TopTwoEI", "Expectation", "LCB",
-           "MaxValueSearch", "ThompsonSampling", "VarianceReduction", "PVRS", "r2_sequence", "sb_sequence"]
+           "MaxValueSearch", "ThompsonSampling", "VarianceReduction", "PVRS", "r2_sequence", "sb_sequence",
+           "BayesSearchCV"]

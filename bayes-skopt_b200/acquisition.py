@@ -16,7 +16,7 @@ from sklearn.utils import check_random_state
 from . import _lib
 from ._engine import Engine
 
-__all__ = ["evaluate_acquisitions", "ExpectedImprovement", "TopTwoEI", "Expectation", "LCB",
+__all__ = ["argmax_acquisition", "evaluate_acquisitions", "ExpectedImprovement", "TopTwoEI", "Expectation", "LCB",
            "MaxValueSearch", "ThompsonSampling", "VarianceReduction", "PVRS"]
 
 _util_engine = None
@@ -300,3 +300,39 @@ def evaluate_acquisitions(X, gpr, acquisition_functions=None, n_samples=10, prog
                     acq_output[j] += tmp / n_samples
     _check_pd()
     return acq_output
+
+
+def argmax_acquisition(X, gpr, acq, n_samples=10, random_state=None, process_group=None, **kwargs):
+    """Index of the candidate that maximises ONE acquisition function -- the tail of ``Optimizer.tell``
+    (bask/optimizer.py:365-380: evaluate_acquisitions(...).flatten() followed by np.argmax).
+
+    For the built-in (mu, std) acquisitions on one GPU nothing but the index leaves the device: thetas are
+    picked and MaxValueSearch's Gumbel variates drawn on the host in the reference's order, then
+    factorise -> sweep -> acquisition epilogue -> finite-guarded theta-mean -> ``bgp_argmax`` (numpy's
+    first-maximum tie rule) run back to back on the engine's stream and 8 bytes come back.  Everything else
+    (full-GP and sample acquisitions, user-defined classes, a process group, n_samples == 0) goes through
+    ``evaluate_acquisitions`` and ``np.argmax`` -- same values, same index."""
+    builtin = isinstance(acq, _DeviceUncertainty) and type(acq).__call__ is _DeviceUncertainty.__call__
+    sharded = process_group is not None and torch.distributed.get_world_size(process_group) > 1
+    if not builtin or sharded or n_samples <= 0:
+        vals = evaluate_acquisitions(X, gpr, (acq,), n_samples=n_samples, progress=False, random_state=random_state,
+                                     process_group=process_group, **kwargs)
+        return int(np.argmax(vals.flatten()))
+    X = np.asarray(X, dtype=np.float64)
+    random_state = check_random_state(random_state)
+    picks = random_state.choice(len(gpr.chain_), replace=False, size=n_samples)
+    e = gpr._eng()
+    gumbel = None
+    if isinstance(acq, MaxValueSearch):
+        gumbel = np.stack([gumbel32_like_reference(acq._params(kwargs)[1]) for _ in picks])
+    f = e.factorize(e.to_dev(gpr.chain_[picks]))
+    mu, sd, _, _ = e.predict(f, e.to_dev(X), noise_off=True, y_mean=float(np.atleast_1d(gpr.y_train_mean_)[0]),
+                             y_std=float(np.atleast_1d(gpr.y_train_std_)[0]))
+    out, _per, _skipped, _ = acq.device_eval(e, mu, sd, kwargs, gumbel=gumbel)
+    idx = e.argmax(out)
+    e.sync()
+    if np.any(f.info.cpu().numpy() != 0):
+        raise np.linalg.LinAlgError(
+            "The kernel, %s, is not returning a positive definite matrix. Try gradually increasing "
+            "the 'alpha' parameter of your GaussianProcessRegressor estimator." % gpr.kernel_)
+    return int(idx.cpu().numpy()[0])

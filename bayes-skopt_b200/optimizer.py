@@ -1,10 +1,9 @@
-"""Ask/tell driver: the reference's ``Optimizer.__init__/ask/tell/run`` (bask/optimizer.py:
-120-445) on the B200 path.  ``ask`` does no maths -- it returns the point computed at the tail of
-``tell`` (candidate generation -> evaluate_acquisitions -> argmax), exactly like the reference.
-
-Out of scope here: the Steinerberger initial design (``init_strategy="sb"``
-falls back to the R2 sequence with a warning-free note in the docstring), the post-hoc
-optimality diagnostics, and BayesSearchCV."""
+"""Ask/tell driver with the reference's surface (``Optimizer.__init__/ask/tell/run`` and the optimality
+diagnostics, bask/optimizer.py:120-689) on the B200 path.  ``ask`` does no maths: it hands out the
+initial design (R2 or Steinerberger sequence, bask/init.py) and afterwards the point computed at the tail
+of the last ``tell`` (hyper-posterior on device -> candidates -> device acquisition sweep -> device argmax).
+Behaviour -- argument meaning, RNG consumption order, exception types -- follows the reference; the code
+is organised around the device path (see ``Optimizer``)."""
 import warnings
 
 import numpy as np
@@ -87,129 +86,153 @@ def sb_sequence(n, d, existing_points=None, random_state=None, restarts=20):
     return np.array(pts)
 
 
+class _InitialDesign:
+    """Where the points come from while no surrogate exists yet (bask/optimizer.py:140-152, 197-219):
+    "r2" -- a pre-computed additive-recurrence sequence, handed out back to front; "sb" -- Steinerberger's
+    greedy sequence, extended by one point against everything told so far; anything else -- uniform draws."""
+
+    def __init__(self, strategy, space, n_points, rng):
+        self.strategy, self.space = strategy, space
+        self._r2 = None
+        self._rng = None
+        if strategy == "r2":
+            self._r2 = space.inverse_transform(r2_sequence(n=max(n_points, 1), d=space.n_dims))
+        elif strategy == "sb":
+            self._rng = np.random.RandomState(rng.randint(2 ** 31))   # its own stream, seeded once
+
+    def point(self, n_remaining, told):
+        if self.strategy == "r2":
+            return self._r2[n_remaining - 1]
+        if self.strategy == "sb":
+            placed = self.space.transform(told) if len(told) > 0 else None
+            seq = sb_sequence(n=len(told) + 1, d=self.space.transformed_n_dims, existing_points=placed,
+                              random_state=self._rng.randint(2 ** 31))
+            return self.space.inverse_transform(np.atleast_2d(seq[len(told)]))[0]
+        return self.space.rvs()[0]
+
+
+class _Observations:
+    """The told points: inputs (original space), targets and per-point noise variances."""
+
+    def __init__(self):
+        self.X, self.y, self.noise = [], [], []
+
+    def clear(self):
+        del self.X[:], self.y[:], self.noise[:]
+
+    def add(self, x, y, noise):
+        """One observation (x a point, y a number) or a batch (x a list of points, y a list); returns how
+        many were added.  Raises ValueError for mismatched shapes, like bask/optimizer.py:287-321."""
+        if is_listlike(y) and is_2Dlistlike(x):
+            if noise is None:
+                noise = [0.0] * len(y)
+            elif not is_listlike(noise) or len(noise) != len(y):
+                raise ValueError("Vector of noise variances needs to be of equal length as `y`.")
+            self.X.extend(x), self.y.extend(y), self.noise.extend(noise)
+            return len(y)
+        if is_listlike(x):
+            if is_listlike(noise):
+                raise ValueError("Vector of noise variances is a list, while tell only received one datapoint.")
+            self.X.append(x), self.y.append(y), self.noise.append(0.0 if noise is None else noise)
+            return 1
+        raise ValueError(f"Type of arguments `x` ({type(x)}) and `y` ({type(y)}) not compatible.")
+
+
 class Optimizer:
-    """Stepwise Bayesian optimisation with a fully Bayesian GP (see bask/optimizer.py:35-119 for
-    the parameters)."""
+    """Stepwise Bayesian optimisation with a fully Bayesian GP -- the reference's ask/tell surface
+    (bask/optimizer.py:35-445; parameters as documented there :35-119), organised around four steps:
+    an initial-design provider, the observation store, ``_refit`` (hyper-posterior on device) and
+    ``_propose`` (candidates -> device acquisition sweep -> device argmax)."""
 
     def __init__(self, dimensions, n_points=500, n_initial_points=10, init_strategy="sb", gp_kernel=None,
                  gp_kwargs=None, gp_priors=None, acq_func="pvrs", acq_func_kwargs=None, random_state=None,
                  **kwargs):
         self.rng = check_random_state(random_state)
-        if callable(acq_func):
-            self.acq_func = acq_func
-        else:
-            self.acq_func = ACQUISITION_FUNC[acq_func]
-        if acq_func_kwargs is None:
-            acq_func_kwargs = {}
-        self.acq_func_kwargs = acq_func_kwargs
+        self.acq_func = acq_func if callable(acq_func) else ACQUISITION_FUNC[acq_func]
+        self.acq_func_kwargs = dict(acq_func_kwargs or {})
         self.space = normalize_dimensions(dimensions)
-        self._n_initial_points = n_initial_points
-        self.n_initial_points_ = n_initial_points
-        self.init_strategy = init_strategy
-        if self.init_strategy == "r2":
-            self._initial_points = self.space.inverse_transform(
-                r2_sequence(n=max(n_initial_points, 1), d=self.space.n_dims))
-        elif self.init_strategy == "sb":
-            self._init_rng = np.random.RandomState(self.rng.randint(2 ** 31))
         self.n_points = n_points
-        if gp_kwargs is None:
-            gp_kwargs = {}
-        if gp_kernel is None:
-            gp_kernel = construct_default_kernel(list(range(self.space.transformed_n_dims)))
-        self.gp = BayesGPR(kernel=gp_kernel, random_state=self.rng.randint(0, np.iinfo(np.int32).max),
-                           **gp_kwargs)
+        self.init_strategy = init_strategy
+        self.n_initial_points_ = n_initial_points          # as configured
+        self._n_initial_points = n_initial_points          # still to be told before the first fit
+        self._design = _InitialDesign(init_strategy, self.space, n_initial_points, self.rng)
+        kernel = gp_kernel if gp_kernel is not None else \
+            construct_default_kernel(list(range(self.space.transformed_n_dims)))
+        self.gp = BayesGPR(kernel=kernel, random_state=self.rng.randint(0, np.iinfo(np.int32).max),
+                           **(gp_kwargs or {}))
         self.gp_priors = gp_priors
-        self.Xi = []
-        self.yi = []
-        self.noisei = []
+        self._obs = _Observations()
         self._next_x = None
 
+    # the reference exposes the told data as plain lists
+    Xi = property(lambda self: self._obs.X, lambda self, v: setattr(self._obs, "X", list(v)))
+    yi = property(lambda self: self._obs.y, lambda self, v: setattr(self._obs, "y", list(v)))
+    noisei = property(lambda self: self._obs.noise, lambda self, v: setattr(self._obs, "noise", list(v)))
+
     def ask(self, n_points=1):
-        """Next point to evaluate (bask/optimizer.py:177-226)."""
+        """Next point to evaluate: from the initial design while it lasts, afterwards the maximiser computed
+        at the tail of the last ``tell`` (bask/optimizer.py:177-226)."""
         if n_points > 1:
             raise NotImplementedError("Returning multiple points is not implemented yet.")
         if self._n_initial_points > 0:
-            if self.init_strategy == "r2":
-                return self._initial_points[self._n_initial_points - 1]
-            if self.init_strategy == "sb":
-                existing = self.space.transform(self.Xi) if len(self.Xi) > 0 else None
-                points = sb_sequence(n=len(self.Xi) + 1, d=self.space.transformed_n_dims,
-                                     existing_points=existing, random_state=self._init_rng.randint(2 ** 31))
-                return self.space.inverse_transform(np.atleast_2d(points[len(self.Xi)]))[0]
-            return self.space.rvs()[0]
+            return self._design.point(self._n_initial_points, self._obs.X)
         if not self.gp.kernel_:
             raise RuntimeError("Initialization is finished, but no model has been fit.")
         return self._next_x
 
     def tell(self, x, y, noise_vector=None, fit=True, replace=False, n_samples=0, gp_samples=100,
              gp_burnin=10, progress=False):
-        """Adds observations, re-samples the hyper-posterior on device and computes the next
-        point (bask/optimizer.py:228-380)."""
+        """Records observations; once the initial design is used up (and ``fit``) re-samples the hyper-
+        posterior and computes the next proposal (bask/optimizer.py:228-380).  Returns an OptimizeResult."""
         if replace:
-            self.Xi = []
-            self.yi = []
-            self.noisei = []
+            self._obs.clear()
             self._n_initial_points = self.n_initial_points_
-        if is_listlike(y) and is_2Dlistlike(x):
-            self.Xi.extend(x)
-            self.yi.extend(y)
-            if noise_vector is None:
-                noise_vector = [0.0] * len(y)
-            elif not is_listlike(noise_vector) or len(noise_vector) != len(y):
-                raise ValueError("Vector of noise variances needs to be of equal length as `y`.")
-            self.noisei.extend(noise_vector)
-            self._n_initial_points -= len(y)
-        elif is_listlike(x):
-            self.Xi.append(x)
-            self.yi.append(y)
-            if noise_vector is None:
-                noise_vector = 0.0
-            elif is_listlike(noise_vector):
-                raise ValueError("Vector of noise variances is a list, while tell only received one datapoint.")
-            self.noisei.append(noise_vector)
-            self._n_initial_points -= 1
-        else:
-            raise ValueError(f"Type of arguments `x` ({type(x)}) and `y` ({type(y)}) not compatible.")
-
+        self._n_initial_points -= self._obs.add(x, y, noise_vector)
         if fit and self._n_initial_points <= 0:
-            if self.gp_priors is not None and len(self.gp_priors) != self.space.transformed_n_dims + 2:
-                raise ValueError("The number of priors does not match the number of dimensions + 2.")
-            with warnings.catch_warnings():
-                warnings.simplefilter("ignore")
-                if self.gp.pos_ is None or replace:
-                    self.gp.fit(self.space.transform(self.Xi), self.yi, noise_vector=np.array(self.noisei),
-                                priors=self.gp_priors, n_desired_samples=gp_samples, n_burnin=gp_burnin,
-                                progress=progress)
-                else:
-                    self.gp.sample(self.space.transform(self.Xi), self.yi, noise_vector=np.array(self.noisei),
-                                   priors=self.gp_priors, n_desired_samples=gp_samples, n_burnin=gp_burnin,
-                                   progress=progress)
-            if self.gp.warp_inputs:
-                # candidates uniform in the warped space, mapped back (bask/optimizer.py:353-357)
-                X_warped = self.rng.uniform(size=(self.n_points, self.space.transformed_n_dims))
-                X = self.gp.unwarp(X_warped)
-            else:
-                X = self.space.transform(self.space.rvs(n_samples=self.n_points, random_state=self.rng))
-            acq_values = evaluate_acquisitions(
-                X=X, gpr=self.gp, acquisition_functions=(self.acq_func,), n_samples=n_samples, progress=False,
-                random_state=self.rng.randint(0, np.iinfo(np.int32).max), **self.acq_func_kwargs).flatten()
-            self._next_x = self.space.inverse_transform(X[np.argmax(acq_values)].reshape((1, -1)))[0]
-        return create_result(self.Xi, self.yi, self.space, self.rng, models=[self.gp])
+            self._refit(gp_samples, gp_burnin, progress, from_scratch=replace)
+            self._next_x = self._propose(n_samples)
+        return self.get_result()
+
+    def _refit(self, gp_samples, gp_burnin, progress, from_scratch):
+        """First call (or ``replace``): MAP start + MCMC (``fit``); later calls continue the ensemble from
+        its last positions on the grown data set (``sample``) -- bask/optimizer.py:323-351."""
+        if self.gp_priors is not None and len(self.gp_priors) != self.space.transformed_n_dims + 2:
+            raise ValueError("The number of priors does not match the number of dimensions + 2.")
+        step = self.gp.fit if (self.gp.pos_ is None or from_scratch) else self.gp.sample
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            step(self.space.transform(self._obs.X), self._obs.y, noise_vector=np.array(self._obs.noise),
+                 priors=self.gp_priors, n_desired_samples=gp_samples, n_burnin=gp_burnin, progress=progress)
+
+    def _candidates(self):
+        """``n_points`` random candidates in the transformed space; with input warping they are uniform in
+        the WARPED space and mapped back (bask/optimizer.py:353-363)."""
+        if self.gp.warp_inputs:
+            return self.gp.unwarp(self.rng.uniform(size=(self.n_points, self.space.transformed_n_dims)))
+        return self.space.transform(self.space.rvs(n_samples=self.n_points, random_state=self.rng))
+
+    def _propose(self, n_samples):
+        """Candidate with the largest acquisition value, back in the original space.  For the built-in
+        (mu, std) acquisitions values and argmax stay on the device; only the index comes back."""
+        X = self._candidates()
+        best = acquisition.argmax_acquisition(X, self.gp, self.acq_func, n_samples=n_samples,
+                                              random_state=self.rng.randint(0, np.iinfo(np.int32).max),
+                                              **self.acq_func_kwargs)
+        return self.space.inverse_transform(X[best].reshape((1, -1)))[0]
+
+    def get_result(self):
+        return create_result(self._obs.X, self._obs.y, self.space, self.rng, models=[self.gp])
 
     def run(self, func, n_iter=1, replace=False, n_samples=5, gp_samples=100, gp_burnin=10):
-        """ask -> func -> tell loop (bask/optimizer.py:382-445)."""
-        for _ in range(n_iter):
+        """``n_iter`` rounds of ask -> func -> tell; ``func`` returns a value or a (value, noise variance)
+        pair (bask/optimizer.py:382-445)."""
+        for it in range(n_iter):
             x = self.ask()
             out = func(x)
-            if hasattr(out, "__len__"):
-                val, noise = out
-            else:
-                val = out
-                noise = 0.0
-            self.tell(x, val, noise_vector=noise, n_samples=n_samples, gp_samples=gp_samples,
-                      gp_burnin=gp_burnin, replace=replace)
-            replace = False
-        return create_result(self.Xi, self.yi, self.space, self.rng, models=[self.gp])
+            val, noise = out if hasattr(out, "__len__") else (out, 0.0)
+            self.tell(x, val, noise_vector=noise, n_samples=n_samples, gp_samples=gp_samples, gp_burnin=gp_burnin,
+                      replace=replace and it == 0)
+        return self.get_result()
 
     # ------------------------------------------------------------------ diagnostics (SURVEY 8f N2)
     def _expected_optimum(self, n_random_starts, random_state):
@@ -220,7 +243,7 @@ class Optimizer:
             key = (len(self.Xi), getattr(self.gp, "chain_generation_", id(self.gp.chain_)), int(random_state), int(n_random_starts))
             if getattr(self, "_expected_optimum_cache", (None, None))[0] == key:
                 return self._expected_optimum_cache[1]
-        result = create_result(self.Xi, self.yi, self.space, self.rng, models=[self.gp])
+        result = self.get_result()
         x = expected_minimum(result, random_state=random_state, n_random_starts=n_random_starts)[0]
         if key is not None:
             self._expected_optimum_cache = (key, x)

@@ -201,11 +201,17 @@ def g4():
 
 def g5():
     """Long reference MCMC on config 1: posterior moments of theta for the distributional check."""
-    print("G5: long reference chain on config 1 (100 walkers x 300 steps after 100 burn-in)")
+    print("G5: long reference chain on config 1 (100 walkers x 2000 steps after 200 burn-in)")
     w = W.config1()
-    gp = fitted_reference_gp(w, n_desired=100 * 300, n_burnin=100, seed=11)
+    gp = fitted_reference_gp(w, n_desired=100 * 2000, n_burnin=200, seed=11)
     d = dict(chain_mean=gp.chain_.mean(axis=0), chain_std=gp.chain_.std(axis=0),
-             chain_len=np.array([len(gp.chain_)]), chain_thin=gp.chain_[::50].copy())
+             chain_len=np.array([len(gp.chain_)]), chain_thin=gp.chain_[::200].copy())
+    # per-step ensemble statistics (the chain is step-major: 2000 steps x 100 walkers): what the
+    # autocorrelation-aware standard errors of the GPU test are computed from, and the acceptance rate
+    steps = gp.chain_.reshape(-1, w.n_walkers, gp.chain_.shape[1])
+    d["step_means"] = steps.mean(axis=1)
+    d["step_sqdev"] = ((steps - d["chain_mean"]) ** 2).mean(axis=1)
+    d["acceptance"] = np.atleast_1d(np.mean(np.any(np.diff(steps, axis=0) != 0.0, axis=2)))
     np.savez_compressed(os.path.join(HERE, "g5_branin_long_chain.npz"), **d)
 
 

@@ -1,6 +1,7 @@
 """CPU: host-side pieces of the optimiser diagnostics: expected_minimum and hdi.
 The reference takes both from third-party packages (skopt.utils.expected_minimum, arviz.hdi)."""
 import numpy as np
+import pytest
 
 import bask_b200.space as S
 
@@ -135,3 +136,22 @@ def test_diagnostics_arithmetic_with_a_stub_gp():
     gap = opt.expected_optimality_gap(n_probabilities=15, n_space_samples=60, n_gp_samples=40, n_random_starts=2,
                                       random_state=3)
     assert np.isfinite(gap) and 0.0 <= gap <= max(opt.yi) - min(opt.yi)
+
+
+def test_bayes_search_cv_search_space_forms():
+    """BayesSearchCV (bask/searchcv.py) host logic: the three accepted forms of search_spaces, sorted-name
+    dimension order, scikit-learn estimator protocol (get_params / clone).  No device work."""
+    from sklearn.base import clone
+    from sklearn.linear_model import Ridge
+
+    from bask_b200.searchcv import BayesSearchCV, dimensions_aslist, point_asdict
+    one = {"alpha": (1e-3, 1e2, "log-uniform"), "fit_intercept": [True, False]}
+    s = BayesSearchCV(Ridge(), one, n_iter=7)
+    assert s.total_iterations == 7 and clone(s).n_iter == 7
+    assert BayesSearchCV(Ridge(), [one, one], n_iter=4).total_iterations == 8
+    assert BayesSearchCV(Ridge(), [(one, 3), (one, 2)]).total_iterations == 5
+    assert dimensions_aslist(one) == [one["alpha"], one["fit_intercept"]]
+    assert point_asdict(one, [0.5, False]) == {"alpha": 0.5, "fit_intercept": False}
+    for bad in ([], [(one, 0)], [{}], 5):
+        with pytest.raises((TypeError, ValueError)):
+            BayesSearchCV(Ridge(), bad).total_iterations  # noqa: B018

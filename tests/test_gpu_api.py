@@ -121,18 +121,40 @@ def test_joint_draws_distribution(bask, g1):
     assert ts.shape == (1, 48) and np.all(np.isfinite(ts))
 
 
+def _batch_means_se(per_step, batch=100):
+    """Standard error of the mean of an autocorrelated per-step series by the method of batch means
+    (batches of `batch` consecutive ensemble steps -- longer than the ensemble's autocorrelation time, which
+    is a few tens of steps on this target -- 20 batches per chain)."""
+    nb = per_step.shape[0] // batch
+    bm = per_step[: nb * batch].reshape(nb, batch, -1).mean(axis=1)
+    return bm.std(axis=0, ddof=1) / np.sqrt(nb)
+
+
 def test_mcmc_posterior_matches_reference_chain(bask, g5):
-    """Device stretch move vs the reference's emcee chain on config 1: posterior means of theta
-    agree within Monte-Carlo error (different RNG, same target)."""
+    """Device stretch move vs the reference's emcee chain on config 1 (different RNG, same target): per
+    hyper-parameter z-tests of the posterior mean and of the posterior variance with autocorrelation-aware
+    standard errors (batch means over ensemble steps, both chains), and the acceptance rate -- which is what
+    a mis-scaled stretch factor or a wrong z^(p-1) Jacobian would move."""
     w = W.config1()
     gp = bask.BayesGPR(kernel=bask.construct_default_kernel([0, 1]), normalize_y=True, random_state=3)
-    gp.fit(w.X, w.y, noise_vector=w.noise_vector, n_desired_samples=100 * 400, n_burnin=200,
+    gp.fit(w.X, w.y, noise_vector=w.noise_vector, n_desired_samples=100 * 2000, n_burnin=200,
            n_walkers_per_thread=100, progress=False)
-    assert gp.chain_.shape == (40000, 4)
-    mean, std = gp.chain_.mean(axis=0), gp.chain_.std(axis=0)
-    np.testing.assert_allclose(mean, g5["chain_mean"], atol=0.12 * g5["chain_std"].max())
-    np.testing.assert_allclose(std, g5["chain_std"], rtol=0.15)
-    assert 0.2 < gp._acceptance.mean() < 0.8
+    assert gp.chain_.shape == (200000, 4)
+    steps = gp.chain_.reshape(-1, 100, 4)
+    ref_mean = g5["chain_mean"]
+    mine_m, ref_m = steps.mean(axis=1), g5["step_means"]
+    z_mean = (mine_m.mean(axis=0) - ref_m.mean(axis=0)) / np.hypot(_batch_means_se(mine_m), _batch_means_se(ref_m))
+    assert np.all(np.abs(z_mean) < 4.0), z_mean
+    mine_v, ref_v = ((steps - ref_mean) ** 2).mean(axis=1), g5["step_sqdev"]
+    z_var = (mine_v.mean(axis=0) - ref_v.mean(axis=0)) / np.hypot(_batch_means_se(mine_v), _batch_means_se(ref_v))
+    assert np.all(np.abs(z_var) < 4.0), z_var
+    # the old, looser moment checks stay as a guard against a degenerate standard-error estimate
+    np.testing.assert_allclose(gp.chain_.mean(axis=0), ref_mean, atol=0.12 * g5["chain_std"].max())
+    np.testing.assert_allclose(gp.chain_.std(axis=0), g5["chain_std"], rtol=0.15)
+    acc_ref = float(g5["acceptance"][0])
+    acc = float(np.mean(np.any(np.diff(steps, axis=0) != 0.0, axis=2)))
+    assert abs(acc - acc_ref) < 0.03, (acc, acc_ref)
+    assert abs(gp._acceptance.mean() - acc_ref) < 0.03
 
 
 # ---- the reference's own behavioural tests (tests/test_bayesgpr.py, tests/test_optimizer.py) ----
@@ -249,3 +271,57 @@ def test_optimizer_diagnostics(bask):
     assert iv[0][:, 0].min() <= 0.5 + 0.8 and iv[0][:, 1].max() >= 0.5 - 0.8
     uni = opt.optimum_intervals(hdi_prob=0.9, multimodal=False, opt_samples=100, space_samples=300, random_state=0)
     assert all(np.asarray(a).shape == (2,) and a[0] <= a[1] for a in uni)
+
+
+# ---- N2: the reference's golden diagnostics (tests/test_optimizer.py:85-140), within Monte-Carlo tolerance ----
+def _told_optimizer(bask, seed):
+    opt = bask.Optimizer(dimensions=[(-2.0, 2.0)], n_initial_points=0, random_state=seed)
+    opt.tell([[-2.0], [-1.0], [0.0], [1.0], [2.0]], [2.0, 0.0, -2.0, 0.0, 2.0], gp_burnin=10)
+    return opt
+
+
+@pytest.mark.parametrize("kw,expected", [(dict(normalized_scores=False, threshold=1.0), 0.99),
+                                         (dict(normalized_scores=False, threshold=(0.9, 0.5)), (0.98, 0.86)),
+                                         (dict(normalized_scores=True, threshold=1.0), 0.99)])
+def test_probability_of_optimality_reference_values(bask, kw, expected):
+    """The reference pins these to 2 decimals for ITS random stream; with the device stream (other MCMC draws,
+    Cholesky instead of SVD joint draws) they hold within Monte-Carlo error: 200 joint draws give a standard
+    error of sqrt(p (1 - p) / 200) <= 0.025 on a probability, plus the chain-to-chain variation of the point
+    estimate -- averaged over three seeds here."""
+    vals = []
+    for seed in (0, 1, 2):
+        opt = _told_optimizer(bask, seed)
+        vals.append(np.atleast_1d(opt.probability_of_optimality(threshold=kw["threshold"], n_random_starts=100,
+                                                                random_state=seed,
+                                                                normalized_scores=kw["normalized_scores"])))
+    got = np.mean(vals, axis=0)
+    np.testing.assert_allclose(got, np.atleast_1d(expected), atol=0.05)
+
+
+@pytest.mark.parametrize("kw,expected", [(dict(normalized_scores=False, use_mean_gp=True), 0.3),
+                                         (dict(normalized_scores=True, use_mean_gp=True), 0.25),
+                                         (dict(normalized_scores=True, use_mean_gp=False), 0.29)])
+def test_expected_optimality_gap_reference_values(bask, kw, expected):
+    vals = []
+    for seed in (0, 1, 2):
+        opt = _told_optimizer(bask, seed)
+        vals.append(opt.expected_optimality_gap(random_state=seed, n_probabilities=10, n_space_samples=100,
+                                                n_gp_samples=100, n_random_starts=10, tol=0.1, **kw))
+    assert abs(np.mean(vals) - expected) < 0.08, vals
+
+
+def test_bayes_search_cv_finds_a_good_ridge_penalty(bask):
+    """N4: BayesSearchCV drives Optimizer.ask/tell with cross-validated scores (bask/searchcv.py:292-354)."""
+    from sklearn.linear_model import Ridge
+    r = np.random.RandomState(0)
+    X = r.randn(120, 30)
+    y = X[:, :3] @ np.array([1.0, -2.0, 0.5]) + 0.5 * r.randn(120)
+    search = bask.BayesSearchCV(Ridge(), {"alpha": (1e-3, 1e3, "log-uniform")}, n_iter=9, cv=3, random_state=0,
+                                optimizer_kwargs=dict(n_initial_points=4, init_strategy="r2", acq_func="ei",
+                                                      n_points=200, n_samples=3, gp_samples=60, gp_burnin=3))
+    search.fit(X, y)
+    assert len(search.cv_results_["params"]) == 9 and len(search.optimizer_results_) == 1
+    assert 1e-3 <= search.best_params_["alpha"] <= 1e3
+    assert search.best_score_ >= max(search.cv_results_["mean_test_score"]) - 1e-12
+    assert search.best_score_ > 0.7 and hasattr(search, "best_estimator_")
+    assert len(search.optimizer_results_[0].x_iters) == 9
