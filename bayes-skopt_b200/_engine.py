@@ -13,6 +13,11 @@ from ._lib import Op, Prior, check
 _F64 = torch.float64
 
 
+def nvtx_range(name):
+    """NVTX range around a host-side phase ("bgp.<phase>"): shows up on the timeline of any CUDA profiler."""
+    return torch.cuda.nvtx.range(name)
+
+
 def _ptr(t):
     return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
 

@@ -14,7 +14,7 @@ import torch
 from sklearn.utils import check_random_state
 
 from . import _lib
-from ._engine import Engine
+from ._engine import Engine, nvtx_range
 
 __all__ = ["argmax_acquisition", "evaluate_acquisitions", "ExpectedImprovement", "TopTwoEI", "Expectation", "LCB",
            "MaxValueSearch", "ThompsonSampling", "VarianceReduction", "PVRS"]
@@ -193,6 +193,17 @@ class PVRS(FullGPAcquisition):
 
 def evaluate_acquisitions(X, gpr, acquisition_functions=None, n_samples=10, progress=False,
                           random_state=None, process_group=None, **kwargs):
+    with nvtx_range("bgp.evaluate_acquisitions"):
+        return _evaluate_acquisitions(X, gpr, acquisition_functions, n_samples, progress, random_state,
+                                      process_group, **kwargs)
+
+
+evaluate_acquisitions.__doc__ = """Evaluates acquisition functions on candidate points, averaged over ``n_samples`` draws from the
+hyper-posterior chain (bask/acquisition.py:48-147); see ``_evaluate_acquisitions``."""
+
+
+def _evaluate_acquisitions(X, gpr, acquisition_functions=None, n_samples=10, progress=False,
+                           random_state=None, process_group=None, **kwargs):
     """Evaluates acquisition functions on candidate points, averaged over ``n_samples`` draws
     from the hyper-posterior chain.  Same arguments, RNG consumption and output as
     bask/acquisition.py:48-147; returns ``(len(acquisition_functions), len(X))`` float64.
@@ -325,12 +336,13 @@ def argmax_acquisition(X, gpr, acq, n_samples=10, random_state=None, process_gro
     gumbel = None
     if isinstance(acq, MaxValueSearch):
         gumbel = np.stack([gumbel32_like_reference(acq._params(kwargs)[1]) for _ in picks])
-    f = e.factorize(e.to_dev(gpr.chain_[picks]))
-    mu, sd, _, _ = e.predict(f, e.to_dev(X), noise_off=True, y_mean=float(np.atleast_1d(gpr.y_train_mean_)[0]),
-                             y_std=float(np.atleast_1d(gpr.y_train_std_)[0]))
-    out, _per, _skipped, _ = acq.device_eval(e, mu, sd, kwargs, gumbel=gumbel)
-    idx = e.argmax(out)
-    e.sync()
+    with nvtx_range("bgp.argmax_acquisition"):
+        f = e.factorize(e.to_dev(gpr.chain_[picks]))
+        mu, sd, _, _ = e.predict(f, e.to_dev(X), noise_off=True, y_mean=float(np.atleast_1d(gpr.y_train_mean_)[0]),
+                                 y_std=float(np.atleast_1d(gpr.y_train_std_)[0]))
+        out, _per, _skipped, _ = acq.device_eval(e, mu, sd, kwargs, gumbel=gumbel)
+        idx = e.argmax(out)
+        e.sync()
     if np.any(f.info.cpu().numpy() != 0):
         raise np.linalg.LinAlgError(
             "The kernel, %s, is not returning a positive definite matrix. Try gradually increasing "

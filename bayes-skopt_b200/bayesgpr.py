@@ -28,7 +28,7 @@ from sklearn.gaussian_process.kernels import RBF, ConstantKernel, WhiteKernel
 from sklearn.utils import check_random_state
 
 from . import _lib
-from ._engine import Engine, find_zeroable_white
+from ._engine import Engine, find_zeroable_white, nvtx_range
 from .priors import as_device_priors
 from .utils import geometric_median, guess_priors, validate_zeroone
 
@@ -502,7 +502,8 @@ class BayesGPR:
             y_std = np.std(y, axis=0)
             noise_vector = np.array(noise_vector) / np.power(y_std, 2)
         self._apply_noise_vector(len(y), noise_vector)
-        self._fit_map(X, y)
+        with nvtx_range("bgp.fit.map"):
+            self._fit_map(X, y)
         self.sample(n_threads=n_threads, n_desired_samples=n_desired_samples, n_burnin=n_burnin,
                     n_walkers_per_thread=n_walkers_per_thread, progress=progress, priors=priors,
                     warp_priors=warp_priors, position=position, add=False, process_group=process_group,

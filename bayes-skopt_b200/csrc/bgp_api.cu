@@ -1,5 +1,6 @@
 // C ABI of libbgp (include/bgp.h): handle, argument checking, workspace, CUDA-graph cache.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>

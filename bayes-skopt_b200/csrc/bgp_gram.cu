@@ -44,13 +44,13 @@ __global__ void __launch_bounds__(256) scale_x_kernel(GramArgs A) {
 }
 
 // CTA (32-row chunk of panel k, theta b): 32 x 32 entries of the lower triangle.  A warp takes
-// four rows (four independent sqrt/exp chains; 32 registers, full occupancy), lanes are the 32 columns.  Chunks of all panels
+// four rows (four independent sqrt/exp chains; 64 registers -- at 40 the kernel spilled ~700k instructions per launch), lanes are the 32 columns.  Chunks of all panels
 // are enumerated along blockIdx.x so that every CTA has the same amount of work.
 constexpr int GRAM_RB = 4;                 // rows per warp
 constexpr int GRAM_ROWS = 8 * GRAM_RB;     // rows per CTA
 __host__ __device__ inline int gram_chunks(int n, int k) { return (n - 32 * k + GRAM_ROWS - 1) / GRAM_ROWS; }
 
-__global__ void __launch_bounds__(256, 6) gram_kernel(GramArgs A) {
+__global__ void __launch_bounds__(256, 4) gram_kernel(GramArgs A) {
   __shared__ DevProgram PR;
   __shared__ ThetaParams TP;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
