@@ -33,6 +33,16 @@ def _worker(rank, world, port, q):
     np.random.seed(w.mes_seed)
     out = bask_b200.evaluate_acquisitions(g["Xc"][:499], gp, acqs, n_samples=10, random_state=1,
                                           process_group=dist.group.WORLD)
+    # the same with the factorisations shared (every rank factorises S / world thetas and the slabs are
+    # all-gathered): forced here, by default only large problems (config 5) take this route
+    from bask_b200.distributed import DeviceBackend
+    DeviceBackend.SHARE_FACTORS_ABOVE_BYTES = 0
+    np.random.seed(w.mes_seed)
+    out_shared = bask_b200.evaluate_acquisitions(g["Xc"][:499], gp, acqs, n_samples=9, random_state=1,
+                                                 process_group=dist.group.WORLD)
+    DeviceBackend.SHARE_FACTORS_ABOVE_BYTES = 96 << 20
+    np.random.seed(w.mes_seed)
+    single9 = bask_b200.evaluate_acquisitions(g["Xc"][:499], gp, acqs, n_samples=9, random_state=1)
     np.random.seed(w.mes_seed)
     single = bask_b200.evaluate_acquisitions(g["Xc"][:499], gp, acqs, n_samples=10, random_state=1)
     # walker-sharded MCMC replays the same Philox stream as the single-GPU graph: identical chains
@@ -44,7 +54,7 @@ def _worker(rank, world, port, q):
                              random_state=5, device=rank)
     gp3.fit(w.X, w.y, noise_vector=w.noise_vector, n_desired_samples=200, n_burnin=3, n_walkers_per_thread=100,
             progress=False)
-    q.put((rank, out, single, gp2.chain_, gp3.chain_))
+    q.put((rank, out, single, gp2.chain_, gp3.chain_, out_shared, single9))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -68,5 +78,7 @@ def test_sharded_equals_single_gpu():
     for j, name in enumerate(["ei", "ttei", "lcb", "mean", "mes"]):
         np.testing.assert_allclose(res[0][1][j], res[0][2][j], rtol=1e-12, atol=1e-300, err_msg=name)
         assert np.argmax(res[0][1][j]) == np.argmax(res[0][2][j])
+        np.testing.assert_allclose(res[0][5][j], res[0][6][j], rtol=1e-12, atol=1e-300, err_msg=name + " (shared factors)")
+    np.testing.assert_array_equal(res[0][5], res[1][5])
     np.testing.assert_array_equal(res[0][3], res[1][3])          # same chain on both ranks
     np.testing.assert_allclose(res[0][3], res[0][4], rtol=1e-12)  # and the same as the one-GPU graph
