@@ -652,6 +652,10 @@ class BayesGPR:
         return e.to_host(mu)[0]
 
     # ------------------------------------------------------------------ joint draws
+    # joint draws over more points than this factor the posterior covariance with the chip-wide blocked
+    # Cholesky (bgp_dense_cholesky_inplace) instead of the one-cluster kernel
+    _JOINT_DRAW_BIG_M = 1024
+
     def _joint_draws_dev(self, Xd, thetas_dev, factor, eps, noise):
         """eps: (S, m, ns) standard normals on device -> (S, m, ns) draws."""
         import torch
@@ -663,24 +667,39 @@ class BayesGPR:
                                   y_std=y_std, want_v=True)
         out = e.empty(S, m, ns)
         cov = e.empty(m, m)
-        slab = e.empty(int(e.lib.bgp_dense_slab_doubles(m)))
+        big = m > self._JOINT_DRAW_BIG_M      # one large matrix: whole-chip blocked factorisation, in place
+        slab = None if big else e.empty(int(e.lib.bgp_dense_slab_doubles(m)))
         info = e.empty(1, dtype=torch.int32)
         for s in range(S):
-            _lib.check(e.lib.bgp_posterior_cov(e.h, thetas_dev[s].data_ptr(), v[s].data_ptr(), Xd.data_ptr(), m,
-                                               v.shape[2], 0 if noise else 1, y_std, cov.data_ptr(), m, e._st),
-                       "bgp_posterior_cov")
+            def build_cov():
+                _lib.check(e.lib.bgp_posterior_cov(e.h, thetas_dev[s].data_ptr(), v[s].data_ptr(), Xd.data_ptr(), m,
+                                                   v.shape[2], 0 if noise else 1, y_std, cov.data_ptr(), m, e._st),
+                           "bgp_posterior_cov")
+                e.launches += 1
+            build_cov()
             with torch.cuda.stream(e.stream):   # ordered with the kernel that wrote cov
                 scale = float(torch.diagonal(cov).abs().max().item()) or 1.0
-            for jit in (1e-10, 1e-9, 1e-8, 1e-7, 1e-6, 1e-5, 1e-4):
-                _lib.check(e.lib.bgp_dense_cholesky(e.h, cov.data_ptr(), m, m, jit * scale, slab.data_ptr(),
-                                                    info.data_ptr(), e._st), "bgp_dense_cholesky")
-                e.launches += 1
+            for attempt, jit in enumerate((1e-10, 1e-9, 1e-8, 1e-7, 1e-6, 1e-5, 1e-4)):
+                if big:
+                    if attempt > 0:
+                        build_cov()             # the failed in-place attempt overwrote the lower triangle
+                    _lib.check(e.lib.bgp_dense_cholesky_inplace(e.h, cov.data_ptr(), m, m, jit * scale,
+                                                                info.data_ptr(), e._st), "bgp_dense_cholesky_inplace")
+                    e.launches += 2 * ((m + 255) // 256) + 1
+                else:
+                    _lib.check(e.lib.bgp_dense_cholesky(e.h, cov.data_ptr(), m, m, jit * scale, slab.data_ptr(),
+                                                        info.data_ptr(), e._st), "bgp_dense_cholesky")
+                    e.launches += 1
                 if int(e.to_host(info)[0]) == 0:
                     break
             else:
                 raise np.linalg.LinAlgError("posterior covariance is not positive definite even with jitter")
-            _lib.check(e.lib.bgp_slab_trmm(e.h, slab.data_ptr(), m, eps[s].data_ptr(), ns, mu[s].data_ptr(),
-                                           out[s].data_ptr(), e._st), "bgp_slab_trmm")
+            if big:
+                _lib.check(e.lib.bgp_dense_trmm(e.h, cov.data_ptr(), m, m, eps[s].data_ptr(), ns, mu[s].data_ptr(),
+                                                out[s].data_ptr(), e._st), "bgp_dense_trmm")
+            else:
+                _lib.check(e.lib.bgp_slab_trmm(e.h, slab.data_ptr(), m, eps[s].data_ptr(), ns, mu[s].data_ptr(),
+                                               out[s].data_ptr(), e._st), "bgp_slab_trmm")
             e.launches += 2
         return out, v
 

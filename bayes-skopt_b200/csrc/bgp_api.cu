@@ -53,6 +53,8 @@ struct bgp_handle_s {
   DevBuf xt_scratch;         // scaled inputs per resident CTA when they exceed shared memory
   DevBuf acq_scratch, extract_scratch;
   DevBuf sweep_scratch;      // windowed sweep: one k* tile per resident CTA
+  DevBuf big_scratch;        // chip-wide dense Cholesky: slab of one diagonal block + per-block info
+  void* cublas = nullptr;    // cublasHandle_t, created on first use of the chip-wide dense Cholesky
   DevBuf warp_x, warp_xc, warp_xt;   // per-theta warped copies of X / candidates / Thompson points
   DevBuf mc_colour, mc_movers, mc_q, mc_factors, mc_newlp, mc_seed;
   // multi-GPU walker sharding: this rank's exchange block and the peers' blocks as mapped here
@@ -105,6 +107,8 @@ int bgp_destroy(bgp_handle_t h) {
   cudaSetDevice(h->device);
   if (h->graph) cudaGraphExecDestroy(h->graph);
   bgp_peer_close(h);
+  bgp::big_release(&h->cublas);
+  h->big_scratch.release();
   h->xchg.release();
   for (DevBuf* b : {&h->prog, &h->fixed_ls, &h->priors, &h->X, &h->y, &h->alpha, &h->slabs_scratch, &h->xt_scratch,
                     &h->acq_scratch, &h->extract_scratch, &h->sweep_scratch, &h->warp_x, &h->warp_xc, &h->warp_xt, &h->mc_colour, &h->mc_movers, &h->mc_q,
@@ -523,6 +527,26 @@ int bgp_dense_cholesky(bgp_handle_t h, const double* a_dev, int m, int64_t lda, 
   A.dense = a_dev; A.ldd = lda; A.jitter = jitter;
   CUDA_TRY(bgp::launch_chol(A, 1, h->sms, (cudaStream_t)stream));
   return 0;
+}
+
+int bgp_dense_cholesky_inplace(bgp_handle_t h, double* a_dev, int m, int64_t lda, double jitter, int32_t* info_dev,
+                               void* stream) {
+  CHECK_H(h);
+  if (!a_dev || m <= 0 || lda < m || !info_dev) return fail("bad dense-cholesky arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(h->big_scratch.ensure(bgp::big_workspace_bytes(m)));
+  const char* err = bgp::big_cholesky(&h->cublas, a_dev, m, lda, jitter, info_dev, h->big_scratch.p, h->sms,
+                                      (cudaStream_t)stream);
+  return err ? fail(err) : 0;
+}
+
+int bgp_dense_trmm(bgp_handle_t h, const double* l_dev, int m, int64_t lda, const double* e_dev, int ns,
+                   const double* mean_dev, double* out_dev, void* stream) {
+  CHECK_H(h);
+  if (!l_dev || m <= 0 || lda < m || !e_dev || ns <= 0 || !out_dev) return fail("bad trmm arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const char* err = bgp::big_trmm(&h->cublas, l_dev, m, lda, e_dev, ns, mean_dev, out_dev, (cudaStream_t)stream);
+  return err ? fail(err) : 0;
 }
 
 int bgp_slab_trmm(bgp_handle_t h, const double* slab_dev, int m, const double* e_dev, int ns,

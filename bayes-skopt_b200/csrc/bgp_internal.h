@@ -164,6 +164,13 @@ cudaError_t launch_pvrs_combine(const CombineArgs& A, cudaStream_t stream);
 cudaError_t launch_vr_combine(const CombineArgs& A, double* scratch, cudaStream_t stream);
 cudaError_t launch_slab_trmm(const double* slab, int m, const double* E, int ns, const double* mean,
                              double* out, cudaStream_t stream);
+// chip-wide dense Cholesky of one large matrix + the draw that uses it (bgp_big.cu); nullptr or an error text
+size_t big_workspace_bytes(int m);
+const char* big_cholesky(void** cublas_handle, double* a, int m, long long lda, double jitter, int32_t* info,
+                         void* workspace, int sms, cudaStream_t stream);
+const char* big_trmm(void** cublas_handle, const double* l, int m, long long lda, const double* e, int ns,
+                     const double* mean, double* out, cudaStream_t stream);
+void big_release(void** cublas_handle);
 cudaError_t launch_argmax(const double* v, int m, long long* idx, double* scratch, cudaStream_t stream);
 
 cudaError_t launch_split(int W, uint64_t seed, const uint64_t* seed_ptr, int step, int32_t* colour,

@@ -157,6 +157,15 @@ int bgp_posterior_cov(bgp_handle_t h, const double* theta_dev, const double* v_d
 int64_t bgp_dense_slab_doubles(int m);
 int bgp_dense_cholesky(bgp_handle_t h, const double* a_dev, int m, int64_t lda, double jitter,
                        double* slab_dev, int32_t* info_dev, void* stream);
+/* Chip-wide variant for one LARGE matrix (thousands of candidates): factors a_dev + jitter*I in place
+ * (row-major, lower triangle read and overwritten with L; the strictly upper part is left alone) by
+ * 256-column blocks -- diagonal blocks on the library's own DMMA kernel, block-column solve and trailing
+ * update as cuBLAS dtrsm / dsyrk (bound lazily; every other entry point is free of library calls) --
+ * and bgp_dense_trmm draws out = mean + L e from it. */
+int bgp_dense_cholesky_inplace(bgp_handle_t h, double* a_dev, int m, int64_t lda, double jitter,
+                               int32_t* info_dev, void* stream);
+int bgp_dense_trmm(bgp_handle_t h, const double* l_dev, int m, int64_t lda, const double* e_dev, int ns,
+                   const double* mean_dev, double* out_dev, void* stream);
 int bgp_slab_trmm(bgp_handle_t h, const double* slab_dev, int m, const double* e_dev, int ns,
                   const double* mean_dev, double* out_dev, void* stream);
 

@@ -325,3 +325,50 @@ def test_bayes_search_cv_finds_a_good_ridge_penalty(bask):
     assert search.best_score_ >= max(search.cv_results_["mean_test_score"]) - 1e-12
     assert search.best_score_ > 0.7 and hasattr(search, "best_estimator_")
     assert len(search.optimizer_results_[0].x_iters) == 9
+
+
+def test_chip_wide_dense_cholesky_and_draw(bask):
+    """bgp_dense_cholesky_inplace / bgp_dense_trmm (own DMMA kernel on the 256-blocks of the diagonal, cuBLAS
+    dtrsm / dsyrk / dtrmm for the rest) against LAPACK on a well-conditioned SPD matrix whose size is not a
+    multiple of the block, and LAPACK's info convention for a matrix that is not positive definite."""
+    import ctypes as C
+    import torch
+    from bask_b200 import _lib
+    from bask_b200._engine import Engine
+    e = Engine()
+    r = np.random.RandomState(0)
+    m, ns = 1100, 7
+    G0 = r.randn(m, m + 50)
+    A = G0 @ G0.T / m + 0.5 * np.eye(m)
+    Ad = e.to_dev(A)
+    info = e.empty(1, dtype=torch.int32)
+    _lib.check(e.lib.bgp_dense_cholesky_inplace(e.h, Ad.data_ptr(), m, m, 0.0, info.data_ptr(), e._st), "chol")
+    assert int(e.to_host(info)[0]) == 0
+    L = np.tril(e.to_host(Ad))
+    np.testing.assert_allclose(L, np.linalg.cholesky(A), rtol=1e-9, atol=1e-11)
+    np.testing.assert_array_equal(np.triu(e.to_host(Ad), 1), np.triu(A, 1))      # upper part untouched
+    E_, mean = r.randn(m, ns), r.randn(m)
+    out, Ed, md = e.empty(m, ns), e.to_dev(E_), e.to_dev(mean)      # (named: the pointers must stay alive)
+    _lib.check(e.lib.bgp_dense_trmm(e.h, Ad.data_ptr(), m, m, Ed.data_ptr(), ns, md.data_ptr(), out.data_ptr(),
+                                    e._st), "trmm")
+    np.testing.assert_allclose(e.to_host(out), mean[:, None] + L @ E_, rtol=1e-10, atol=1e-10)
+    bad = A.copy()
+    bad[700, 700] = -1.0                       # the 701st leading minor is the first that fails
+    Bd = e.to_dev(bad)
+    _lib.check(e.lib.bgp_dense_cholesky_inplace(e.h, Bd.data_ptr(), m, m, 0.0, info.data_ptr(), e._st), "chol")
+    assert int(e.to_host(info)[0]) == 701
+
+
+def test_joint_draws_large_candidate_set_uses_the_chip_wide_factorisation(bask, g1):
+    """sample_y over 1 500 points (> _JOINT_DRAW_BIG_M): same draws as the one-cluster path for the same
+    normals (up to the conditioning of the jittered covariance), finite, right shape."""
+    w = W.config1()
+    gp = bask.BayesGPR(kernel=bask.construct_default_kernel([0, 1]), normalize_y=True, random_state=0)
+    gp.fit(w.X, w.y, noise_vector=w.noise_vector, n_desired_samples=100, n_burnin=2, n_walkers_per_thread=100,
+           progress=False)
+    X = np.random.RandomState(3).uniform(size=(1500, 2))
+    big = gp.sample_y(X, sample_mean=True, n_samples=4, random_state=1)
+    gp._JOINT_DRAW_BIG_M = 10 ** 9
+    small = gp.sample_y(X, sample_mean=True, n_samples=4, random_state=1)
+    assert big.shape == (1500, 4) and np.all(np.isfinite(big))
+    np.testing.assert_allclose(big, small, atol=1e-4 * np.abs(small).max())
