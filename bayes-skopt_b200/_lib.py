@@ -62,6 +62,8 @@ _SIGNATURES = {
     "bgp_pvrs_combine": [_P, _P, _P, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P],
     "bgp_vr_combine": [_P, _P, C.c_int, C.c_int64, _P, _P, _P, _P, _P],
     "bgp_slab_trmm": [_P, _P, C.c_int, _P, C.c_int, _P, _P, _P],
+    "bgp_acq_sweep_nccl": [_P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P, C.c_int, C.c_double, _P, C.c_int,
+                           C.c_double, C.c_double, _P, _P, _P],
     "bgp_dense_cholesky_inplace": [_P, _P, C.c_int, C.c_int64, C.c_double, _P, _P],
     "bgp_dense_trmm": [_P, _P, C.c_int, C.c_int64, _P, C.c_int, _P, _P, _P],
     "bgp_peer_export": [_P, C.c_int, _P],

@@ -53,6 +53,7 @@ struct bgp_handle_s {
   DevBuf xt_scratch;         // scaled inputs per resident CTA when they exceed shared memory
   DevBuf acq_scratch, extract_scratch;
   DevBuf sweep_scratch;      // windowed sweep: one k* tile per resident CTA
+  DevBuf nccl_scratch;       // multi-GPU C entry point: moments, per-theta values, gather buffers
   DevBuf big_scratch;        // chip-wide dense Cholesky: slab of one diagonal block + per-block info
   void* cublas = nullptr;    // cublasHandle_t, created on first use of the chip-wide dense Cholesky
   DevBuf warp_x, warp_xc, warp_xt;   // per-theta warped copies of X / candidates / Thompson points
@@ -109,6 +110,7 @@ int bgp_destroy(bgp_handle_t h) {
   bgp_peer_close(h);
   bgp::big_release(&h->cublas);
   h->big_scratch.release();
+  h->nccl_scratch.release();
   h->xchg.release();
   for (DevBuf* b : {&h->prog, &h->fixed_ls, &h->priors, &h->X, &h->y, &h->alpha, &h->slabs_scratch, &h->xt_scratch,
                     &h->acq_scratch, &h->extract_scratch, &h->sweep_scratch, &h->warp_x, &h->warp_xc, &h->warp_xt, &h->mc_colour, &h->mc_movers, &h->mc_q,
@@ -486,6 +488,81 @@ int bgp_acq_combine(bgp_handle_t h, const double* per_theta_dev, int S, int m, c
   if (!per_theta_dev || S <= 0 || m <= 0 || !skipped_dev || !out_dev) return fail("bad combine arguments");
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(bgp::launch_acq_combine(per_theta_dev, S, m, skipped_dev, out_dev, (cudaStream_t)stream));
+  return 0;
+}
+
+/* ---- multi-GPU sweep for C callers: candidates sharded over the ranks of an ncclComm_t ---- */
+#define NCCL_TRY(expr) do { int _r = (expr); if (_r != 0) { \
+    g_err = std::string(#expr) + ": " + (N->error_string ? N->error_string(_r) : "NCCL error"); return -1; } } while (0)
+
+int bgp_acq_sweep_nccl(bgp_handle_t h, void* nccl_comm, int rank, int world, int kind, const double* theta_dev, int S,
+                       const double* slabs_dev, const double* z_dev, const double* Xc_all_dev, int m_total, double p0,
+                       const float* g32_dev, int K, double y_mean, double y_std, double* out_dev, int64_t* argmax_dev,
+                       void* stream) {
+  CHECK_H(h);
+  if (ready(h)) return -1;
+  if (!nccl_comm || world <= 0 || rank < 0 || rank >= world) return fail("bad communicator arguments");
+  if (!theta_dev || S <= 0 || S > 1024 || !slabs_dev || !z_dev || !Xc_all_dev || m_total < world || !out_dev)
+    return fail("bad sharded-sweep arguments (every rank needs at least one candidate)");
+  if (kind < BGP_ACQ_EI || kind > BGP_ACQ_MES) return fail("unknown acquisition");
+  if (kind == BGP_ACQ_MES && (!g32_dev || K <= 0)) return fail("MES needs the float32 Gumbel variates");
+  bgp::NcclApi* N = bgp::nccl_api();
+  if (!N) return fail("libnccl.so.2 could not be loaded");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int q = m_total / world, rem = m_total % world;
+  const int lo = rank * q + (rank < rem ? rank : rem), m_loc = q + (rank < rem ? 1 : 0), m_max = q + (rem ? 1 : 0);
+  const int F64 = bgp::nccl_dtype_f64(), I32 = bgp::nccl_dtype_i32();
+  // workspace: mu, sd, per-theta (S x m_loc each) | send (S x m_max) | gathered (world x S x m_max) |
+  // mu_all, sd_all (S x m_total each, MES) | stats S x 4 | yopt S | fit S x 5 | ref S x 4 | allref world x S x 4 |
+  // local values m_loc | skipped S (int32)
+  const size_t Sm = (size_t)S * m_loc, Smax = (size_t)S * m_max, Sall = (size_t)S * m_total;
+  size_t need = 3 * Sm + Smax + (size_t)world * Smax + 2 * Sall + (size_t)S * (4 + 1 + 5 + 4) + (size_t)world * S * 4 +
+                m_loc + S + 16;
+  CUDA_TRY(h->nccl_scratch.ensure(sizeof(double) * need));
+  double* w = h->nccl_scratch.as<double>();
+  double *mu = w, *sd = mu + Sm, *per = sd + Sm, *send = per + Sm, *gath = send + Smax, *mu_all = gath + (size_t)world * Smax,
+         *sd_all = mu_all + Sall, *stats = sd_all + Sall, *yopt = stats + (size_t)S * 4, *fit = yopt + S,
+         *ref = fit + (size_t)S * 5, *allref = ref + (size_t)S * 4, *vals = allref + (size_t)world * S * 4;
+  int32_t* skipped = reinterpret_cast<int32_t*>(vals + m_loc);
+
+  if (bgp_predict_batched(h, theta_dev, S, slabs_dev, z_dev, Xc_all_dev + (size_t)lo * h->d, m_loc, 1, y_mean, y_std, mu, sd,
+                          nullptr, 0, nullptr, nullptr, 0, stream)) return -1;
+  auto gather_rows = [&](const double* src, int rows, double* dst_all) -> int {
+    // (rows x m_loc) blocks of every rank -> (rows x m_total) on every rank
+    CUDA_TRY(bgp::launch_pad_rows(src, rows, m_loc, send, m_max, st));
+    NCCL_TRY(N->all_gather(send, gath, (size_t)rows * m_max, F64, nccl_comm, st));
+    CUDA_TRY(bgp::launch_unpack_rows(gath, world, rows, m_max, m_total, dst_all, st));
+    return 0;
+  };
+  const double* yopt_p = nullptr;
+  const double* ref_p = nullptr;
+  const double* fit_p = nullptr;
+  if ((kind == BGP_ACQ_EI || kind == BGP_ACQ_TTEI) && isnan(p0)) {
+    // y_opt = min over ALL candidates of the posterior mean, per theta (bask/acquisition.py:166-167)
+    if (bgp_acq_stats(h, mu, sd, S, m_loc, stats, stream)) return -1;
+    CUDA_TRY(bgp::launch_column0(stats, S, 4, yopt, st));
+    NCCL_TRY(N->all_reduce(yopt, yopt, (size_t)S, F64, bgp::nccl_op_min(), nccl_comm, st));
+    yopt_p = yopt;
+  }
+  if (kind == BGP_ACQ_TTEI) {
+    if (bgp_ei_best(h, mu, sd, S, m_loc, p0, yopt_p, (int64_t)lo, ref, stream)) return -1;
+    NCCL_TRY(N->all_gather(ref, allref, (size_t)S * 4, F64, nccl_comm, st));
+    CUDA_TRY(bgp::launch_ttei_pick(allref, world, S, ref, st));
+    ref_p = ref;
+  }
+  if (kind == BGP_ACQ_MES) {
+    // the Gumbel fit needs the moments of all candidates: gathered, then fitted on every rank (same bits)
+    if (gather_rows(mu, S, mu_all) || gather_rows(sd, S, sd_all)) return -1;
+    if (bgp_mes_fit(h, mu_all, sd_all, S, m_total, fit, stream)) return -1;
+    fit_p = fit;
+  }
+  if (bgp_acq_per_theta(h, kind, mu, sd, S, m_loc, p0, yopt_p, ref_p, g32_dev, K, fit_p, per, skipped, stream)) return -1;
+  // a theta is dropped if ANY candidate anywhere is non-finite (bask/acquisition.py:140-141)
+  NCCL_TRY(N->all_reduce(skipped, skipped, (size_t)S, I32, bgp::nccl_op_max(), nccl_comm, st));
+  if (bgp_acq_combine(h, per, S, m_loc, skipped, vals, stream)) return -1;
+  if (gather_rows(vals, 1, out_dev)) return -1;
+  if (argmax_dev && bgp_argmax(h, out_dev, m_total, argmax_dev, stream)) return -1;
   return 0;
 }
 

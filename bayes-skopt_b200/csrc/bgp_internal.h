@@ -171,6 +171,23 @@ const char* big_cholesky(void** cublas_handle, double* a, int m, long long lda, 
 const char* big_trmm(void** cublas_handle, const double* l, int m, long long lda, const double* e, int ns,
                      const double* mean, double* out, cudaStream_t stream);
 void big_release(void** cublas_handle);
+// lazily bound NCCL (bgp_nccl.cu) for the multi-GPU C entry point
+struct NcclApi {
+  int (*all_reduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*all_gather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  const char* (*error_string)(int) = nullptr;
+  bool ok = false;
+};
+NcclApi* nccl_api();
+int nccl_dtype_f64();
+int nccl_dtype_i32();
+int nccl_op_min();
+int nccl_op_max();
+cudaError_t launch_pad_rows(const double* src, int S, int m_loc, double* dst, int m_max, cudaStream_t st);
+cudaError_t launch_unpack_rows(const double* gathered, int world, int S, int m_max, int m_total, double* out,
+                               cudaStream_t st);
+cudaError_t launch_column0(const double* stats, int S, int stride, double* out, cudaStream_t st);
+cudaError_t launch_ttei_pick(const double* allref, int world, int S, double* best, cudaStream_t st);
 cudaError_t launch_argmax(const double* v, int m, long long* idx, double* scratch, cudaStream_t stream);
 
 cudaError_t launch_split(int W, uint64_t seed, const uint64_t* seed_ptr, int step, int32_t* colour,

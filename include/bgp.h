@@ -222,6 +222,23 @@ int bgp_acq_combine(bgp_handle_t h, const double* per_theta_dev, int S, int m,
 /* argmax with numpy tie-breaking (first maximum), bask/optimizer.py:374-376 */
 int bgp_argmax(bgp_handle_t h, const double* v_dev, int m, int64_t* idx_dev, void* stream);
 
+/* ---- multi-GPU sweep for C callers ---------------------------------------------------
+ * One call per rank (one process / handle per GPU), `nccl_comm` an ncclComm_t over the `world` ranks created by
+ * the caller.  Every rank passes the same thetas (with their factorisations, bgp_factorize_batched), the FULL
+ * candidate array (m_total x d) and, for MaxValueSearch, the same Gumbel variates; it sweeps only its contiguous
+ * block of candidates (the first m_total % world ranks take one more) and exchanges what evaluate_acquisitions
+ * (bask/acquisition.py:48-147) needs globally: the per-theta min mean (EI's default y_opt, all-reduce MIN), the
+ * per-theta EI maximiser (TopTwoEI, all-gather), the moments for the Gumbel fit (MaxValueSearch, all-gather), the
+ * non-finite flags (all-reduce MAX) and finally the values.  out_dev (m_total) and argmax_dev (may be NULL)
+ * are identical on every rank and equal to the single-GPU bgp_acq_sweep on the whole candidate set.  NCCL is
+ * bound at run time (dlopen "libnccl.so.2"), so the communicator and these calls share one NCCL instance with
+ * the host application.  The walker-sharded MCMC needs no NCCL at all: bgp_peer_export / bgp_peer_connect /
+ * bgp_mcmc_run_sharded exchange log-probabilities by peer stores. */
+int bgp_acq_sweep_nccl(bgp_handle_t h, void* nccl_comm, int rank, int world, int kind,
+                       const double* theta_dev, int S, const double* slabs_dev, const double* z_dev,
+                       const double* Xc_all_dev, int m_total, double p0, const float* g32_dev, int K,
+                       double y_mean, double y_std, double* out_dev, int64_t* argmax_dev, void* stream);
+
 /* ---- K3: emcee-equivalent stretch move on device (bask/bayesgpr.py:510-530) ---------
  * pos (W x p) in/out, lp (W) out; chain (T x W x p) and lp_chain (T x W) step-major like
  * EnsembleSampler.get_chain; accepted (W) counts.  Philox-4x32-10 keyed by `seed`; the
