@@ -17,8 +17,6 @@ Bs = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [64, 256
 rows = []
 for n in ns:
     for B in Bs:
-        if n >= 4096 and B > 256:
-            continue
         w, thetas = W.config4(n, B)
         e = Engine()
         k = construct_default_kernel(list(range(w.d))) + WhiteKernel()
@@ -26,7 +24,7 @@ for n in ns:
         e.set_data(w.X, (w.y - w.y.mean()) / w.y.std(), 1e-10)
         th = e.to_dev(thetas)
         lp, _, info = e.logprob_dev(th); e.sync()
-        reps = 3 if n >= 2048 else 10
+        reps = 2 if n >= 4096 else (3 if n >= 2048 else 10)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(e.stream)
         for _ in range(reps):
