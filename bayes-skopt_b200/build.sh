@@ -5,7 +5,7 @@ cd "$(dirname "$0")"
 mkdir -p build
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC"
 pids=""
-for f in bgp_api bgp_gram bgp_chol bgp_small bgp_sweep bgp_sweep_v1 bgp_acq bgp_mcmc bgp_extract bgp_grad bgp_big bgp_nccl bgp_post; do
+for f in bgp_api bgp_gram bgp_chol bgp_small bgp_sweep bgp_acq bgp_mcmc bgp_extract bgp_grad bgp_big bgp_nccl bgp_post; do
   [ -f csrc/$f.cu ] || continue
   if [ ! -f build/$f.o ] || [ csrc/$f.cu -nt build/$f.o ] || [ csrc/bgp_common.cuh -nt build/$f.o ] \
      || [ csrc/bgp_internal.h -nt build/$f.o ] || [ ../include/bgp.h -nt build/$f.o ]; then

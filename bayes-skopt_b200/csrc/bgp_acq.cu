@@ -10,6 +10,8 @@ namespace bgp {
 
 constexpr int MES_PTS = 192;      // trial points evaluated per refinement round (3 x 64)
 constexpr int MES_CH = 512;       // candidates per block in the quantile search
+constexpr int MES_KL = 8;         // lanes that share one candidate in the MES epilogue
+constexpr int MES_PCH = 8;        // trial points per block (blockIdx.z)
 constexpr int MES_NEWTON = 6;        // quadratic from a 1/63^2 bracket: converged after 3, 6 for margin
 constexpr int ST = 8;             // doubles of per-theta statistics
 constexpr int MS = 16;            // doubles of per-theta MES search state
@@ -179,7 +181,10 @@ __global__ void mes_eval_kernel(const double* __restrict__ mu, const double* __r
   }
   __shared__ double rg[8], rd[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int p = 0; p < npts; ++p) {
+  // the trial points are spread over blockIdx.z in chunks of MES_PCH: with m = 10^4 a (block, theta) grid alone
+  // is 200 CTAs and leaves most of the chip idle for 192 sequential points
+  const int p_begin = blockIdx.z * MES_PCH, p_end = min(npts, p_begin + MES_PCH);
+  for (int p = p_begin; p < p_end; ++p) {
     const double x = pts[s * MES_PTS + p];
     double g = 0.0, dg = 0.0;
 #pragma unroll
@@ -276,19 +281,27 @@ __global__ void mes_epilogue_kernel(const double* __restrict__ mu, const double*
   for (int k = threadIdx.x; k < K; k += blockDim.x)
     maxv[k] = (double)gumbel[(size_t)s * K + k] * beta + alpha;
   __syncthreads();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m) return;
-  const double mean = -mu[(size_t)s * m + i], b = sd[(size_t)s * m + i];
+  // a candidate's K draws are split over MES_KL adjacent lanes (more warps in flight for the long FP64
+  // special-function chains), partial sums combined by a fixed shuffle tree
+  const int i = blockIdx.x * (blockDim.x / MES_KL) + threadIdx.x / MES_KL, kl = threadIdx.x % MES_KL;
+  const bool live = i < m;
+  const double mean = live ? -mu[(size_t)s * m + i] : 0.0, b = live ? sd[(size_t)s * m + i] : 1.0;
   double acc = 0.0;
-  for (int k = 0; k < K; ++k) {
+  for (int k = kl; k < K; k += MES_KL) {
     const double gam = (maxv[k] - mean) / b;
     double term;
     if (gam > 0.0) {
       // one exp shared by phi and Phi: erfc(t) = erfcx(t) exp(-t^2), phi = exp(-t^2) / sqrt(2 pi)
       const double t = gam * 0.7071067811865476;
       const double E = exp(-t * t);
-      const double e = 0.5 * erfcx(t) * E;
-      term = gam * 0.3989422804014327 * E / (2.0 * (1.0 - e)) - log1p(-e);
+      const double e = 0.5 * erfcx(t) * E;                   // 1 - Phi(gamma)
+      if (e < 1e-6) {
+        // far upper tail (gamma > ~4.8, most draws of most candidates): 1/(1-e) and -log1p(-e) by their series,
+        // exact to < 1e-18 relative here -- saves the division and the log1p of the general branch
+        term = gam * 0.3989422804014327 * E * 0.5 * (1.0 + e + e * e) + e * (1.0 + e * (0.5 + e * 0.3333333333333333));
+      } else {
+        term = gam * 0.3989422804014327 * E / (2.0 * (1.0 - e)) - log1p(-e);
+      }
     } else {
       const double t = -gam * 0.7071067811865476;
       if (t < 26.0) {
@@ -302,6 +315,9 @@ __global__ void mes_epilogue_kernel(const double* __restrict__ mu, const double*
     }
     acc += term;
   }
+#pragma unroll
+  for (int o = 1; o < MES_KL; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (!live || kl != 0) return;
   out[(size_t)s * m + i] = acc / K;
 }
 
@@ -370,13 +386,13 @@ cudaError_t launch_mes_fit(const double* mu, const double* sd, int S, int m, dou
                            cudaStream_t stream) {
   AcqScratch w = carve(scratch, S, m);
   const int nblk = (m + MES_CH - 1) / MES_CH;
-  dim3 gq(nblk, S);
-  mes_eval_kernel<<<gq, 256, 0, stream>>>(mu, sd, m, w.pts, 64, 0, w.gpart, w.dpart);
+  auto grid = [&](int npts) { return dim3(nblk, S, (npts + MES_PCH - 1) / MES_PCH); };
+  mes_eval_kernel<<<grid(64), 256, 0, stream>>>(mu, sd, m, w.pts, 64, 0, w.gpart, w.dpart);
   mes_control_kernel<<<S, 32, 0, stream>>>(1, nblk, w.pts, w.gpart, w.dpart, w.st, nullptr);
-  mes_eval_kernel<<<gq, 256, 0, stream>>>(mu, sd, m, w.pts, MES_PTS, 0, w.gpart, w.dpart);
+  mes_eval_kernel<<<grid(MES_PTS), 256, 0, stream>>>(mu, sd, m, w.pts, MES_PTS, 0, w.gpart, w.dpart);
   mes_control_kernel<<<S, 32, 0, stream>>>(2, nblk, w.pts, w.gpart, w.dpart, w.st, nullptr);
   for (int it = 0; it < MES_NEWTON; ++it) {
-    mes_eval_kernel<<<gq, 256, 0, stream>>>(mu, sd, m, w.pts, 3, 1, w.gpart, w.dpart);
+    mes_eval_kernel<<<grid(3), 256, 0, stream>>>(mu, sd, m, w.pts, 3, 1, w.gpart, w.dpart);
     mes_control_kernel<<<S, 32, 0, stream>>>(3, nblk, w.pts, w.gpart, w.dpart, w.st, nullptr);
   }
   mes_control_kernel<<<S, 32, 0, stream>>>(4, nblk, w.pts, w.gpart, w.dpart, w.st, fit_out ? fit_out : w.fit);
@@ -412,7 +428,7 @@ cudaError_t launch_acq_per_theta(const AcqArgs& A, cudaStream_t stream) {
       break;
     case BGP_ACQ_MES: {
       if (!A.u32 || A.K <= 0 || A.K > MES_MAX_K) return cudaErrorInvalidValue;
-      dim3 gm((m + 127) / 128, S);
+      dim3 gm((m + 128 / MES_KL - 1) / (128 / MES_KL), S);
       mes_epilogue_kernel<<<gm, 128, A.K * sizeof(double), stream>>>(A.mu, A.sd, m, A.u32, A.K,
                                                                      A.mes_fit ? A.mes_fit : w.fit, A.per_theta);
     } break;

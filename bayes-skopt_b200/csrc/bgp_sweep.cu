@@ -397,10 +397,7 @@ cudaError_t prepare_sweep() {
   return e;
 }
 
-cudaError_t launch_sweep_v1(const SweepArgs& A, cudaStream_t stream);
-
 cudaError_t launch_sweep(const SweepArgs& A, int sms, cudaStream_t stream) {
-  if (std::getenv("BGP_SWEEP_V1") != nullptr) return launch_sweep_v1(A, stream);   // A/B against the round-1 kernel
   const bool win = sweep_is_windowed(A.n, A.d, A.R, A.n_leaves);
   const size_t smem = sweep_smem(win, A.n, A.d, A.R, A.n_leaves);
   if (smem > SWEEP_SMEM_OPTIN) return cudaErrorInvalidValue;
