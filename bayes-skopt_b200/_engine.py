@@ -186,6 +186,24 @@ class Engine:
     def sync(self):
         self.stream.synchronize()
 
+    def fetch_after(self, event, *tensors):
+        """Host copies of ``tensors`` that wait for ``event`` only: the D2H runs on a side stream,
+        so work enqueued on the engine's stream after the event keeps the GPU busy meanwhile."""
+        if not hasattr(self, "_side"):
+            self._side, self._side_pinned = torch.cuda.Stream(device=self.device), {}
+        self._side.wait_event(event)
+        outs = []
+        with torch.cuda.stream(self._side):
+            for i, t in enumerate(tensors):
+                key = (i, tuple(t.shape), t.dtype)
+                h = self._side_pinned.get(key)
+                if h is None:
+                    h = self._side_pinned[key] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+                h.copy_(t, non_blocking=True)
+                outs.append(h)
+        self._side.synchronize()
+        return [h.numpy().copy() for h in outs]
+
     # ------------------------------------------------------------------ model set-up
     def set_kernel(self, kernel, n_warp=0):
         """Uploads the kernel program.  ``n_warp`` = d switches input warping on: theta rows then
@@ -215,9 +233,11 @@ class Engine:
         X = np.ascontiguousarray(X, dtype=np.float64)
         n, d = X.shape
         alpha = np.ascontiguousarray(np.broadcast_to(np.asarray(alpha, dtype=np.float64), (n,)))
-        Xd, yd, ad = self.to_dev(X), self.to_dev(np.asarray(y, dtype=np.float64).reshape(n)), self.to_dev(alpha)
+        # one staging copy and one H2D for the three arrays; bgp_set_data copies them into the handle's
+        # own buffers in stream order, so nothing here has to wait for the device
+        packed = self.to_dev(np.concatenate([X.reshape(-1), np.asarray(y, dtype=np.float64).reshape(n), alpha]))
+        Xd, yd, ad = packed[: n * d], packed[n * d: n * d + n], packed[n * d + n:]
         check(self.lib.bgp_set_data(self.h, _ptr(Xd), _ptr(yd), _ptr(ad), n, d, self._st), "bgp_set_data")
-        self.stream.synchronize()
         self.n, self.d = n, d
 
     # ------------------------------------------------------------------ K1 + K2

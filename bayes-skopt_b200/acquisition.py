@@ -217,7 +217,7 @@ def _evaluate_acquisitions(X, gpr, acquisition_functions=None, n_samples=10, pro
     n_acqs = len(acquisition_functions)
     acq_output = np.zeros((n_acqs, n_cand_points))
     random_state = check_random_state(random_state)
-    trace_sample_i = random_state.choice(len(gpr.chain_), replace=False, size=n_samples)
+    trace_sample_i = random_state.choice(gpr._chain_len(), replace=False, size=n_samples)
     e = gpr._eng()
     for i_acq, acq in enumerate(acquisition_functions):
         if isinstance(acq, FullGPAcquisition):
@@ -250,7 +250,7 @@ def _evaluate_acquisitions(X, gpr, acquisition_functions=None, n_samples=10, pro
         raise NotImplementedError("user-defined UncertaintyAcquisition classes are not supported with a "
                                   "process_group (they need the moments of all candidates on one rank)")
     if has_unc and not sharded:
-        th = e.to_dev(gpr.chain_[trace_sample_i])
+        th = gpr._chain_rows_dev(trace_sample_i)
         f = e.factorize(th)
         # the positive-definiteness flags are read back after the sweep has been enqueued (see
         # _check_pd below): a host round trip here would leave the GPU idle
@@ -267,7 +267,7 @@ def _evaluate_acquisitions(X, gpr, acquisition_functions=None, n_samples=10, pro
                 gumbels[j].append(gumbel32_like_reference(acq._params(kwargs)[1]))
             elif isinstance(acq, SampleAcquisition) and not sample_drawn:
                 sample_drawn = True
-                ind = random_state.choice(len(gpr.chain_), size=1, replace=True)
+                ind = random_state.choice(gpr._chain_len(), size=1, replace=True)
                 draws.append((int(ind[0]), random_state.standard_normal(size=(1, n_cand_points)).T))
     samples = None
     if has_smp:
@@ -293,6 +293,7 @@ def _evaluate_acquisitions(X, gpr, acquisition_functions=None, n_samples=10, pro
         if isinstance(acq, _DeviceUncertainty) and type(acq).__call__ is _DeviceUncertainty.__call__:
             g = np.stack(gumbels[j]) if j in gumbels else None
             out, _per, _skipped, _ = acq.device_eval(e, mu, sd, kwargs, gumbel=g)
+            gpr._materialize()   # a deferred sample() read-back overlaps the sweep just enqueued
             res = e.to_host(out)
             _check_pd()
             acq_output[j] += res
@@ -331,17 +332,18 @@ def argmax_acquisition(X, gpr, acq, n_samples=10, random_state=None, process_gro
         return int(np.argmax(vals.flatten()))
     X = np.asarray(X, dtype=np.float64)
     random_state = check_random_state(random_state)
-    picks = random_state.choice(len(gpr.chain_), replace=False, size=n_samples)
+    picks = random_state.choice(gpr._chain_len(), replace=False, size=n_samples)
     e = gpr._eng()
     gumbel = None
     if isinstance(acq, MaxValueSearch):
         gumbel = np.stack([gumbel32_like_reference(acq._params(kwargs)[1]) for _ in picks])
     with nvtx_range("bgp.argmax_acquisition"):
-        f = e.factorize(e.to_dev(gpr.chain_[picks]))
+        f = e.factorize(gpr._chain_rows_dev(picks))
         mu, sd, _, _ = e.predict(f, e.to_dev(X), noise_off=True, y_mean=float(np.atleast_1d(gpr.y_train_mean_)[0]),
                                  y_std=float(np.atleast_1d(gpr.y_train_std_)[0]))
         out, _per, _skipped, _ = acq.device_eval(e, mu, sd, kwargs, gumbel=gumbel)
         idx = e.argmax(out)
+        gpr._materialize()   # a deferred sample() read-back overlaps the sweep just enqueued
         e.sync()
     if np.any(f.info.cpu().numpy() != 0):
         raise np.linalg.LinAlgError(

@@ -52,6 +52,12 @@ def _walkers_independent(coords):
     return np.linalg.cond(C.astype(float)) <= 1e8
 
 
+def p_eager():
+    """BGP_EAGER_SAMPLE=1 makes sample() read its results back before returning (debugging aid)."""
+    import os
+    return os.environ.get("BGP_EAGER_SAMPLE", "0") == "1"
+
+
 class BayesGPR:
     """Drop-in for ``bask.BayesGPR`` on one B200.  See the reference docstring
     (bask/bayesgpr.py:19-146) for the meaning of every parameter and attribute."""
@@ -71,6 +77,7 @@ class BayesGPR:
         self.random_state = check_random_state(random_state)
         self.noise = noise
         self.noise_ = None
+        self._pending = None         # device-side result of the last sample() not yet read back
         self.chain_ = None
         self.pos_ = None
         self.kernel_ = None
@@ -82,6 +89,70 @@ class BayesGPR:
         self._prior_key = None
         self.chain_generation_ = 0   # bumped whenever chain_ is replaced (cache keys of the diagnostics)
         self.timings_ = {}           # CUDA-event milliseconds of the last sample(): "mcmc", "factorize"
+
+    # ------------------------------------------------------------------ deferred read-back
+    # sample() on the device path returns as soon as the MCMC graph is enqueued.  chain_, pos_,
+    # kernel_ (whose theta becomes the geometric median of the chain) and everything derived from
+    # them are read back at their first use (`_materialize`): a caller that goes straight on to
+    # evaluate_acquisitions enqueues the sweep behind the chain (theta rows gathered on the
+    # device) and the read-back, the median and the point-estimate factorisation then overlap it.
+    def _lazy(name):   # noqa: N805
+        store = "_lz_" + name
+
+        def get(self):
+            if self._pending is not None:
+                self._materialize()
+            return getattr(self, store, None)
+
+        def put(self, v):
+            if getattr(self, "_pending", None) is not None:
+                self._materialize()
+            setattr(self, store, v)
+        return property(get, put)
+
+    chain_ = _lazy("chain_")
+    pos_ = _lazy("pos_")
+    kernel_ = _lazy("kernel_")
+    timings_ = _lazy("timings_")          # CUDA-event milliseconds of the last sample()
+    _acceptance = _lazy("_acceptance")    # per-walker acceptance fraction of the last sample()
+    del _lazy
+
+    def _n_kernel_theta(self):
+        """len(kernel_.theta) without walking the kernel tree on every call (~0.1 ms in sklearn)."""
+        k = self.kernel_
+        c = getattr(self, "_nk_cache", None)
+        if c is None or c[0] is not k:
+            c = self._nk_cache = (k, len(k.theta))
+        return c[1]
+
+    def _chain_len(self):
+        p = self._pending
+        return p["kept"] * p["W"] if p is not None else len(self.chain_)
+
+    def _chain_rows_dev(self, idx):
+        """Rows ``idx`` of chain_ as a device tensor, without forcing the read-back."""
+        e = self._eng()
+        p = self._pending
+        if p is None:
+            return e.to_dev(self.chain_[idx])
+        import torch
+        idx = np.asarray(idx, dtype=np.int64)
+        flat = (p["first"] + p["n_thin"] * (idx // p["W"])) * p["W"] + idx % p["W"]
+        sel = e.to_dev(flat, dtype=torch.int64)
+        with torch.cuda.stream(e.stream):
+            return p["buf"]["chain"].reshape(-1, p["n_dim"]).index_select(0, sel)
+
+    def _materialize(self):
+        p, self._pending = self._pending, None
+        if p is None:
+            return
+        e = self._eng()
+        buf, ev = p["buf"], p["ev"]
+        chain_steps, pos_out, acc = e.fetch_after(ev[1], buf["chain"], buf["pos"], buf["acc"])
+        self._lz_timings_["mcmc_ms"] = ev[0].elapsed_time(ev[1])
+        self._lz__acceptance = acc / max(p["n_samples"], 1)
+        self._finish_sample(chain_steps, pos_out, p["n_burnin"], p["n_thin"], p["n_dim"], p["n_kernel"],
+                            p["added_dims"], p["add"])
 
     # ------------------------------------------------------------------ engine plumbing
     def _eng(self):
@@ -124,6 +195,8 @@ class BayesGPR:
 
     @property
     def _factor(self):
+        if self._pending is not None:
+            self._materialize()
         f = getattr(self, "_factor_pending", None)
         if f is not None:
             self._factor_pending = None
@@ -138,6 +211,8 @@ class BayesGPR:
 
     @_factor.setter
     def _factor(self, f):
+        if getattr(self, "_pending", None) is not None:
+            self._materialize()
         self._factor_pending = None
         self._factor_value = f
 
@@ -369,7 +444,7 @@ class BayesGPR:
         if data_changed or noise_vector is not None:
             self._upload_model(structure_changed=False)
 
-        n_dim = n_kernel = len(self.theta)
+        n_dim = n_kernel = self._n_kernel_theta()
         if n_walkers is None:
             n_walkers = n_threads * n_walkers_per_thread
         n_samples = int(np.ceil(n_desired_samples / n_walkers) + n_burnin)
@@ -400,11 +475,13 @@ class BayesGPR:
         if n_walkers < 2 * n_dim:
             raise RuntimeError("It is unadvisable to use a red-blue move with fewer walkers than twice "
                                "the number of dimensions.")
-        if not np.all(np.isfinite(pos)):
-            raise ValueError("At least one parameter value was infinite or NaN")
-        if not _walkers_independent(pos):
-            raise ValueError("Initial state has a large condition number. Make sure that your walkers "
-                             "are linearly independent for the best performance")
+
+        def check_initial_state():
+            if not np.all(np.isfinite(pos)):
+                raise ValueError("At least one parameter value was infinite or NaN")
+            if not _walkers_independent(pos):
+                raise ValueError("Initial state has a large condition number. Make sure that your walkers "
+                                 "are linearly independent for the best performance")
 
         e = self._eng()
         table, host_fn = self._prior_table(priors, warp_priors, n_kernel)
@@ -414,6 +491,7 @@ class BayesGPR:
             # walkers sharded over the ranks of the group (one all-gather of W/2 log-probs per half
             # step); every rank ends up with the identical chain
             from .distributed import sharded_mcmc
+            check_initial_state()
             chain_steps, pos_out, accepted = sharded_mcmc(e, pos, n_samples, seed, a, process_group)
             self._acceptance = accepted / max(n_samples, 1)
         elif host_fn is None:
@@ -424,14 +502,27 @@ class BayesGPR:
                 buf = e.mcmc(pos, n_samples, seed, a=a, buffers=self._mc_buffers)
                 ev[1].record(e.stream)
             self._mc_buffers = buf
-            e.sync()
-            self.timings_["mcmc_ms"] = ev[0].elapsed_time(ev[1])
-            self.timings_["mcmc_logprob_evals"] = int(n_walkers * (1 + n_samples))
-            chain_steps = buf["chain"].cpu().numpy()
-            pos_out = buf["pos"].cpu().numpy()
-            self._acceptance = buf["acc"].cpu().numpy() / max(n_samples, 1)
+            # emcee's checks of the initial state (a 128 x p SVD among them) run while the device is
+            # already sampling; a rejected state raises exactly as before and the run is discarded
+            check_initial_state()
+            self._lz_timings_["mcmc_logprob_evals"] = int(n_walkers * (1 + n_samples))
+            first = n_burnin + n_thin - 1
+            self._pending = dict(buf=buf, ev=ev, n_samples=n_samples, n_burnin=n_burnin, n_thin=n_thin,
+                                 n_dim=n_dim, n_kernel=n_kernel, added_dims=added_dims, add=add, W=n_walkers,
+                                 first=first, kept=len(range(first, n_samples, n_thin)))
+            self.chain_generation_ += 1
+            if add or self.warp_inputs or p_eager():
+                self._materialize()
+            return
         else:
+            check_initial_state()
             chain_steps, pos_out = self._host_stepped_mcmc(pos, n_samples, seed, a, host_fn)
+        self.chain_generation_ += 1
+        self._finish_sample(chain_steps, pos_out, n_burnin, n_thin, n_dim, n_kernel, added_dims, add)
+
+    def _finish_sample(self, chain_steps, pos_out, n_burnin, n_thin, n_dim, n_kernel, added_dims, add):
+        """Host tail of sample(): chain bookkeeping, geometric median as the point estimate
+        (bask/bayesgpr.py:531-548)."""
         if not np.all(np.isfinite(chain_steps)):
             raise ValueError("At least one parameter value was infinite or NaN")
         chain = chain_steps[n_burnin + n_thin - 1:: n_thin].reshape(-1, n_dim)
@@ -439,7 +530,6 @@ class BayesGPR:
             self.chain_ = np.concatenate([self.chain_, chain])
         else:
             self.chain_ = chain
-        self.chain_generation_ += 1
         # point estimate: the factorisation at the geometric median is only enqueued here; its
         # LinAlgError check and the LML read-back happen at the first use (no host round trip)
         median = geometric_median(self.chain_)
