@@ -384,6 +384,12 @@ class Engine:
         check(self.lib.bgp_peer_status(self.h, C.byref(flag)), "bgp_peer_status")
         return bool(flag.value)
 
+    def peer_counters(self):
+        """(nanoseconds spent inside peer exchanges, number of exchanges) of this rank so far."""
+        out = (C.c_uint64 * 2)()
+        check(self.lib.bgp_peer_counters(self.h, out), "bgp_peer_counters")
+        return int(out[0]), int(out[1])
+
     # ------------------------------------------------------------------ K3
     def mcmc(self, pos, n_steps, seed, a=2.0, buffers=None):
         """Device-resident run: returns (pos, lp, chain, lp_chain, accepted) tensors."""

@@ -847,6 +847,19 @@ int bgp_peer_close(bgp_handle_t h) {
   return 0;
 }
 
+/* developer counters of the peer exchange: out[0] = nanoseconds this rank spent inside exchanges (stores, fence,
+ * waiting for the slowest peer), out[1] = number of exchanges, since bgp_peer_export */
+int bgp_peer_counters(bgp_handle_t h, unsigned long long* out) {
+  CHECK_H(h);
+  if (!out) return fail("null out");
+  out[0] = out[1] = 0;
+  if (!h->xchg.p) return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemcpy(out, reinterpret_cast<const char*>(h->xchg.p) + sizeof(double) * 2 * (size_t)h->peers.cap +
+                               sizeof(unsigned long long) * 10, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 /* 1 when a peer exchange of this handle ever timed out (a rank died or never launched): the chain of that run
  * is invalid */
 int bgp_peer_status(bgp_handle_t h, int* timed_out) {

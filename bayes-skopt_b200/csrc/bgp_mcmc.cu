@@ -46,17 +46,33 @@ __global__ void propose_kernel(const double* __restrict__ pos, const int32_t* __
   int32_t* mv = lists;
   int32_t* ot = lists + W;
   int32_t* cnt = lists + 2 * W;
+  // position of walker i among the walkers of its colour: ballot prefix inside the warp, warp totals
+  // through shared memory, a running base per block-sized chunk of walkers (O(W) instead of O(W^2))
+  __shared__ int wz[32], wo[32];
   if (threadIdx.x == 0) { cnt[0] = 0; cnt[1] = 0; }
   __syncthreads();
-  for (int i = threadIdx.x; i < W; i += blockDim.x) {
-    const int ci = colour[i];
-    int before = 0;
-    for (int j = 0; j < i; ++j) before += (colour[j] == ci);
-    if (ci == half) { mv[before] = i; atomicAdd(&cnt[0], 1); }
-    else { ot[before] = i; atomicAdd(&cnt[1], 1); }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int c0 = 0; c0 < W; c0 += blockDim.x) {
+    const int i = c0 + threadIdx.x;
+    const int ci = i < W ? colour[i] : -1;
+    const unsigned m0 = __ballot_sync(0xffffffffu, ci == 0), m1 = __ballot_sync(0xffffffffu, ci == 1);
+    if (lane == 0) { wz[wid] = __popc(m0); wo[wid] = __popc(m1); }
+    __syncthreads();
+    int bz = cnt[0], bo = cnt[1], tz = 0, to = 0;   // cnt[0]: walkers of colour 0 so far, cnt[1]: colour 1
+    for (int w = 0; w < nwarps; ++w) {
+      if (w < wid) { bz += wz[w]; bo += wo[w]; }
+      tz += wz[w]; to += wo[w];
+    }
+    const unsigned lt = (1u << lane) - 1u;
+    if (ci >= 0) {
+      const int before = ci == 0 ? bz + __popc(m0 & lt) : bo + __popc(m1 & lt);
+      if (ci == half) mv[before] = i; else ot[before] = i;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { cnt[0] += tz; cnt[1] += to; }
+    __syncthreads();
   }
-  __syncthreads();
-  const int ns = cnt[0], nc = cnt[1];
+  const int ns = cnt[half], nc = cnt[1 - half];
   const uint64_t sd = seed_of(seed, seed_ptr);
   for (int k = threadIdx.x; k < ns; k += blockDim.x) {
     Philox4 r = philox4x32_10(sd, (uint32_t)step, TAG_PROP + (uint32_t)half, (uint32_t)k, 0u);
@@ -110,18 +126,24 @@ __global__ void accept_kernel(double* __restrict__ pos, double* __restrict__ lp,
 // split_kernel keeps W 64-bit sort keys in dynamic shared memory: opt in above the 48 KB default so
 // that the W <= 8192 the API accepts really launches (outside stream capture, from bgp_create)
 cudaError_t prepare_mcmc() {
-  return cudaFuncSetAttribute(split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * (int)sizeof(uint64_t));
+  cudaError_t e = cudaFuncSetAttribute(split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * (int)sizeof(uint64_t));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(propose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (2 * 8192 + 2) * (int)sizeof(int32_t));
+  return e;
 }
 
 cudaError_t launch_split(int W, uint64_t seed, const uint64_t* seed_ptr, int step, int32_t* colour,
                          cudaStream_t stream) {
-  split_kernel<<<1, 256, W * sizeof(uint64_t), stream>>>(W, seed, seed_ptr, step, colour);
+  // the rank of a key is an O(W) scan of shared memory per walker: one thread per walker up to 1024
+  const int nt = W <= 256 ? 256 : (W <= 512 ? 512 : 1024);
+  split_kernel<<<1, nt, W * sizeof(uint64_t), stream>>>(W, seed, seed_ptr, step, colour);
   return cudaGetLastError();
 }
 cudaError_t launch_propose(const double* pos, const int32_t* colour, int W, int p, int half, double a,
                            uint64_t seed, const uint64_t* seed_ptr, int step, double* q, double* factors,
                            int32_t* movers, cudaStream_t stream) {
-  propose_kernel<<<1, 256, (2 * W + 2) * sizeof(int32_t), stream>>>(pos, colour, W, p, half, a, seed,
+  propose_kernel<<<1, W <= 256 ? 256 : 512, (2 * W + 2) * sizeof(int32_t), stream>>>(pos, colour, W, p, half, a, seed,
                                                                       seed_ptr, step, q, factors, movers);
   return cudaGetLastError();
 }
@@ -143,7 +165,8 @@ cudaError_t launch_accept(double* pos, double* lp, const double* q, const double
 // Exchange block of a rank (bgp_peer_export allocates it with cudaMalloc; every peer maps it):
 //   [0, 2 cap)      doubles   two value buffers (epoch parity): slot i = log-prob of proposal i
 //   then 8 + 8 u64            flags[src] = last epoch whose slice from rank `src` is complete;
-//                             word 8 = this rank's own epoch counter, word 9 = time-out flag
+//                             word 8 = this rank's own epoch counter, word 9 = time-out flag,
+//                             words 10 / 11 = nanoseconds spent in exchanges / their number (tooling)
 // A rank may run at most one epoch ahead of a peer (it cannot pass the wait of epoch e + 1 before the
 // peer has published e + 1, which the peer does after it finished reading the buffer of epoch e), so
 // two buffers are enough.
@@ -172,7 +195,8 @@ __device__ const double* peer_exchange(const PeerXchg& X, const double* __restri
   __shared__ unsigned long long ep_s;
   const int tid = threadIdx.x, nt = blockDim.x;
   unsigned long long* my_words = reinterpret_cast<unsigned long long*>(X.block[X.rank] + 2 * (size_t)X.cap);
-  if (tid == 0) ep_s = my_words[8] + 1;
+  unsigned long long t_enter = 0;
+  if (tid == 0) { ep_s = my_words[8] + 1; t_enter = global_ns(); }
   __syncthreads();
   const unsigned long long ep = ep_s;
   const size_t par = (size_t)(ep & 1) * X.cap;
@@ -192,7 +216,11 @@ __device__ const double* peer_exchange(const PeerXchg& X, const double* __restri
     }
   }
   __syncthreads();
-  if (tid == 0) my_words[8] = ep;
+  if (tid == 0) {
+    my_words[8] = ep;
+    my_words[10] += global_ns() - t_enter;   // developer counters: time spent in exchanges, their number
+    my_words[11] += 1;
+  }
   return X.block[X.rank] + par;
 }
 

@@ -445,9 +445,11 @@ def run_b200(args):
     y_mean, y_std = float(gp.y_train_mean_), float(gp.y_train_std_)
     bufs = {"mc": None}
 
-    def device_cycle(seed):
+    def device_cycle(seed, marks=None):
         with torch.cuda.stream(e.stream):
             flush.zero_()
+        if marks is not None:
+            marks[0].record(e.stream)
         if world > 1:
             from bask_b200.distributed import sharded_mcmc_dev
             b = sharded_mcmc_dev(e, pos_dev, T, seed, 2.0, pg, buffers=bufs["mc"])
@@ -456,13 +458,19 @@ def run_b200(args):
         bufs["mc"] = b
         with torch.cuda.stream(e.stream):
             th = b["chain"][-1].index_select(0, picks_dev).contiguous()
+        if marks is not None:
+            marks[1].record(e.stream)
         if sweep is not None:
             out = sweep.evaluate(Xc_dev, th, [(_lib.ACQ_MES, float("nan"))], {0: g32_dev})[0]
-            return e.argmax(out.contiguous())
-        f = e.factorize(th)
-        mu, sd, _, _ = e.predict(f, Xc_dev, noise_off=True, y_mean=y_mean, y_std=y_std)
-        out, _, _, _ = e.acq(_lib.ACQ_MES, mu, sd, gumbel32=g32_dev)
-        return e.argmax(out)
+            r = e.argmax(out.contiguous())
+        else:
+            f = e.factorize(th)
+            mu, sd, _, _ = e.predict(f, Xc_dev, noise_off=True, y_mean=y_mean, y_std=y_std)
+            out, _, _, _ = e.acq(_lib.ACQ_MES, mu, sd, gumbel32=g32_dev)
+            r = e.argmax(out)
+        if marks is not None:
+            marks[2].record(e.stream)
+        return r
 
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
@@ -479,17 +487,36 @@ def run_b200(args):
         t_end = time.time()
         time.sleep(0.15)
     dev_ms = ev0.elapsed_time(ev1) / args.steps
+    # where the device-resident cycle goes (this rank): MCMC (graph) vs factorise + sweep + MES + argmax
+    parts = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(3)]
+    for i, mk in enumerate(parts):
+        device_cycle(300 + i, marks=mk)
+    barrier()
+    part_mcmc = float(np.mean([mk[0].elapsed_time(mk[1]) for mk in parts]))
+    xchg_us = 0.0
+    if world > 1:    # mean time one peer exchange takes on this rank (stores + fence + waiting for the slowest rank)
+        c0 = e.peer_counters()
+        device_cycle(400)
+        barrier()
+        c1 = e.peer_counters()
+        xchg_us = 1e-3 * (c1[0] - c0[0]) / max(c1[1] - c0[1], 1)
+    part_ask = float(np.mean([mk[1].elapsed_time(mk[2]) for mk in parts]))
     launches = (e.launches - l0) // max(args.steps, 1)
     clocks = clk.summary(t_begin, t_end)
 
     # ---------------- end to end through the public API (host buffers in, host results out)
     ask_ms = []
 
-    def e2e_cycle(seed):
+    def e2e_cycle(seed, ask_alone=False):
         with torch.cuda.stream(e.stream):
             flush.zero_()
         gp.sample(w.X, w.y, noise_vector=w.noise_vector, n_desired_samples=Wk, n_burnin=w.n_burnin,
                   n_walkers_per_thread=Wk, process_group=pg)
+        if ask_alone:
+            # ask() latency on its own: sample() returns while the device is still sampling, so the
+            # chain is read back (synchronises) before the clock starts
+            gp.chain_  # noqa: B018
+            e.sync()
         t0 = time.perf_counter()
         vals = bask_b200.evaluate_acquisitions(cands, gp, (mes,), n_samples=S, random_state=seed,
                                                process_group=pg, **w.acq_kwargs)[0]
@@ -506,6 +533,10 @@ def run_b200(args):
         e2e_cycle(10 + i)
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    ask_ms.clear()
+    for i in range(min(args.steps, 5)):
+        e2e_cycle(50 + i, ask_alone=True)
+    barrier()
     h2d = 8 * (w.X.size + 2 * w.n + Wk * (w.d + 2) + cands.size // world + S * (w.d + 2)) + 4 * S * K
     d2h = 8 * (T * Wk * (w.d + 2) + Wk * (w.d + 2) + m_local * world + 1 + S)
 
@@ -530,10 +561,11 @@ def run_b200(args):
     sweep_ms = _timed(e, lambda: e.predict(f, Xc_one, noise_off=True, y_mean=y_mean, y_std=y_std), 5, warm=2)
     sweep_tf = S * m_local * flops_sweep(w.n, w.d) / (sweep_ms * 1e-3) / 1e12
 
-    times = torch.tensor([dev_ms, e2e_ms, float(np.mean(ask_ms))], dtype=torch.float64, device=e.device)
+    times = torch.tensor([dev_ms, e2e_ms, float(np.mean(ask_ms)), part_mcmc, part_ask, xchg_us], dtype=torch.float64,
+                         device=e.device)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, ask_lat = [float(v) for v in times.cpu()]
+    dev_ms, e2e_ms, ask_lat, part_mcmc, part_ask, xchg_us = [float(v) for v in times.cpu()]
 
     c5 = None
     if not args.no_c5:
@@ -560,6 +592,10 @@ def run_b200(args):
                 "lml_evals_per_s_batched": 1024 / (lml_ms * 1e-3),
                 "lml_batched_tflops": 1024 * flops_lml(w.n, w.d) / (lml_ms * 1e-3) / 1e12,
                 "ask_latency_ms": ask_lat,
+                "cycle_breakdown_ms": {"mcmc_graph": part_mcmc, "factorise_sweep_mes_argmax": part_ask,
+                                       "peer_exchange_us": xchg_us,
+                                       "note": "device-resident cycle, CUDA events, max over ranks; peer_exchange_us = "
+                                               "mean time inside one log-prob exchange of the sharded MCMC (N > 1)"},
                 "gpu_launches": int(launches),
                 "roofline": {"kernel": "gram_kernel + chol_lml_kernel (K1+K2: Gram, Cholesky, LML; 64 thetas, n=500)",
                              "bound": "tensor", "achieved": chol_tf, "peak": peak_tf, "unit": "TFLOP/s",

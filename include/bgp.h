@@ -275,12 +275,15 @@ int bgp_mcmc_seed_source(bgp_handle_t h, const uint64_t* seed_dev);
  *   bgp_peer_connect  maps the blocks of all `world` ranks (ipc_handles: world x BGP_IPC_HANDLE_BYTES,
  *                     rank order); world <= 8, one node
  *   bgp_peer_close    unmaps them (before the process group is torn down)
- *   bgp_peer_status   timed_out = 1 when an exchange ever waited longer than 10 s for a peer */
+ *   bgp_peer_status   timed_out = 1 when an exchange ever waited longer than 10 s for a peer
+ *   bgp_peer_counters out[0] = nanoseconds this rank has spent inside exchanges (peer stores, fence, waiting for
+ *                     the slowest rank), out[1] = number of exchanges -- where a sharded run's time goes */
 #define BGP_IPC_HANDLE_BYTES 64
 int bgp_peer_export(bgp_handle_t h, int max_walkers, void* ipc_handle_out);
 int bgp_peer_connect(bgp_handle_t h, const void* ipc_handles, int rank, int world);
 int bgp_peer_close(bgp_handle_t h);
 int bgp_peer_status(bgp_handle_t h, int* timed_out);
+int bgp_peer_counters(bgp_handle_t h, unsigned long long* out);
 int bgp_mcmc_run_sharded(bgp_handle_t h, double* pos_dev, double* lp_dev, int W, int T, double a,
                          uint64_t seed, double* chain_dev, double* lp_chain_dev, int32_t* accepted_dev,
                          void* stream);
