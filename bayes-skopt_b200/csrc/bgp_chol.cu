@@ -144,15 +144,20 @@ __device__ __forceinline__ int warp_potrf32(double* __restrict__ D, double* __re
 // stage rows [c0, c0+32) x the columns of panels [j0, j0+kc) of L into shared memory with
 // cp.async (16-byte LDGSTS, L2 only): every copy of a thread is in flight before the first wait,
 // so the stage costs about one L2 round trip instead of one per loop iteration
-__device__ __forceinline__ void stage_block_row(const double* slab, const SlabGeom& G, double* Bs, int bstride,
-                                                int c0, int j0, int kc, int tid, int nthreads) {
+__device__ __forceinline__ void stage_block_row_issue(const double* slab, const SlabGeom& G, double* Bs, int bstride,
+                                                      int c0, int j0, int kc, int tid, int nthreads) {
   for (int idx = tid; idx < 512 * kc; idx += nthreads) {
     const int c2 = idx & 15, row = (idx >> 4) & 31, jj = idx >> 9;
     const double* src = slab + G.off(j0 + jj) + (size_t)(c0 + row - 32 * (j0 + jj)) * 32 + 2 * c2;
     const unsigned dst = (unsigned)__cvta_generic_to_shared(Bs + (size_t)row * bstride + 32 * jj + 2 * c2);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
   }
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void stage_block_row(const double* slab, const SlabGeom& G, double* Bs, int bstride,
+                                                int c0, int j0, int kc, int tid, int nthreads) {
+  stage_block_row_issue(slab, G, Bs, bstride, c0, j0, kc, tid, nthreads);
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
 
 __device__ __align__(16) const double g_zero16[2] = {0.0, 0.0};
@@ -271,7 +276,8 @@ template <int NTL>
 __device__ __forceinline__ void finish_tiles(double (&acc)[4][4][2], const TileSet& TS, const CholArgs& A,
                                              const double* Lt, const double* Wd, double* slab,
                                              const SlabGeom& G, int k, int n, int npad, int b, int r, int q,
-                                             double& zz, const double2 (&ginit)[2][4]) {
+                                             double& zz, const double2 (&ginit)[2][4], double* Bs_push, int bstride,
+                                             int cs) {
   const int c0 = 32 * k;
 #pragma unroll
   for (int t = 0; t < NTL; ++t) {
@@ -330,6 +336,27 @@ __device__ __forceinline__ void finish_tiles(double (&acc)[4][4][2], const TileS
 #pragma unroll
     for (int u = 0; u < 4; ++u)
       *reinterpret_cast<double2*>(dst + 8 * u) = make_double2(acc[t][u][0], acc[t][u][1]);
+    // rows of block row k+1: this is column block k of the NEXT panel's B operand -- written straight
+    // into the staging buffer of every CTA of the cluster (columns [32k, 32k+32) are not in use during
+    // panel k), so the next panel does not start with an L2 round trip; the end-of-panel barrier
+    // (release / acquire at cluster scope) publishes it
+    if (Bs_push && TS.kind[t] == 0 && TS.rb[t] < c0 + 64) {
+      double* lp = Bs_push + (size_t)(TS.rb[t] - (c0 + 32) + r) * bstride + c0 + 2 * q;
+      if (cs == 1) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) *reinterpret_cast<double2*>(lp + 8 * u) = make_double2(acc[t][u][0], acc[t][u][1]);
+      } else {
+        const unsigned la = (unsigned)__cvta_generic_to_shared(lp);
+        for (int pr = 0; pr < cs; ++pr) {
+          unsigned ra;
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(ra) : "r"(la), "r"(pr));
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};\n" ::"r"(ra + 64 * u), "d"(acc[t][u][0]),
+                         "d"(acc[t][u][1]) : "memory");
+        }
+      }
+    }
     if (TS.kind[t] == 1 && r == 0) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -462,11 +489,17 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
 #pragma unroll
       for (int i = 0; i < 10; ++i) dacc[i][0] = dacc[i][1] = 0.0;
       const int nchunks = (k + kch - 1) / kch;
+      // pre_staged: the previous panel left this panel's block row in Bs -- columns of panels < k-1 by
+      // cp.async issued after its last K-loop, column block k-1 pushed by the warps that solved those rows
+      const bool pre_staged = k > 0 && k <= kch && NW > 1;
+      if (pre_staged) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
       for (int ch = 0; ch < nchunks; ++ch) {
         const int j0 = ch * kch, kc = min(kch, k - j0);
         __syncthreads();
-        stage_block_row(slab, G, Bs, bstride, c0, j0, kc, tid, NW * 32);
-        __syncthreads();
+        if (!pre_staged) {
+          stage_block_row(slab, G, Bs, bstride, c0, j0, kc, tid, NW * 32);
+          __syncthreads();
+        }
         for (int c8 = warp; c8 < 4 * kc; c8 += NW) {
           double2 f[4];
 #pragma unroll
@@ -495,6 +528,8 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
       // it: the trailing-update GEMM of their first round only needs previous panels, so they run
       // it now and meet warp 0 at named barrier 2 right before the panel solve.
       const bool overlap = nchunks <= 1 && NW > 1;
+      // the next panel is pre-staged by this one (see pre_staged above)
+      const bool next_pre = overlap && k + 1 < P && k + 1 <= kch;
       if (warp == 0) {
         int f = warp_potrf32(S.Dblk, S.Lt, &S.Wd[0][0], lane, logdet, min(32, n - c0));
         if (f && lane == 0) S.fail = c0 + f;
@@ -506,6 +541,10 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
                 *reinterpret_cast<const double2*>(S.Lt + (e >> 4) * LS + 2 * (e & 15));
         BGP_STAMP(3);
         if (overlap) asm volatile("bar.sync 2, %0;" ::"r"(NW * 32) : "memory");
+        if (next_pre) {
+          asm volatile("bar.sync 3, %0;" ::"r"(NW * 32) : "memory");   // every K-loop of this panel is done with Bs
+          stage_block_row_issue(slab, G, Bs, bstride, c0 + 32, 0, k, tid, NW * 32);
+        }
       } else if (A.dbg && warp == (A.dbg_tid >> 5)) {
         BGP_STAMP(3);
       }
@@ -586,11 +625,16 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
         }
         BGP_STAMP_ADD(7, tph); tph = clock64();
         if (overlap && rd == 0) asm volatile("bar.sync 2, %0;" ::"r"(NW * 32) : "memory");
+        if (next_pre && rd == rounds - 1) {
+          asm volatile("bar.sync 3, %0;" ::"r"(NW * 32) : "memory");   // every K-loop of this panel is done with Bs
+          stage_block_row_issue(slab, G, Bs, bstride, c0 + 32, 0, k, tid, NW * 32);
+        }
         if (S.fail) continue;
         double zpart = 0.0;
+        double* push = next_pre ? Bs : nullptr;
         switch (ntl) {
-          case 2: finish_tiles<2>(acc, TS, A, S.Lt, &S.Wd[0][0], slab, G, k, n, npad, b, r, q, zpart, ginit); break;
-          case 1: finish_tiles<1>(acc, TS, A, S.Lt, &S.Wd[0][0], slab, G, k, n, npad, b, r, q, zpart, ginit); break;
+          case 2: finish_tiles<2>(acc, TS, A, S.Lt, &S.Wd[0][0], slab, G, k, n, npad, b, r, q, zpart, ginit, push, bstride, CS); break;
+          case 1: finish_tiles<1>(acc, TS, A, S.Lt, &S.Wd[0][0], slab, G, k, n, npad, b, r, q, zpart, ginit, push, bstride, CS); break;
           default: break;
         }
         zz += zpart;
@@ -602,6 +646,7 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
       if (S.fail) break;
     }
 
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");   // a pre-stage issued before a failed panel
     // ------------------------------------------------------------------ epilogue
     zz = warp_sum(zz);
     if (warp == 0) logdet = warp_sum(logdet);

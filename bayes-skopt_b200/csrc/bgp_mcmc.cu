@@ -17,9 +17,13 @@ __device__ __forceinline__ uint64_t seed_of(uint64_t seed, const uint64_t* seed_
 }
 
 // colour[i] = 0 for a uniformly random subset of ceil(W/2) walkers, 1 for the rest
-// (emcee: inds = arange(W) % 2; random.shuffle(inds)).
-__global__ void split_kernel(int W, uint64_t seed, const uint64_t* seed_ptr, int step,
-                             int32_t* __restrict__ colour) {
+// (emcee: inds = arange(W) % 2; random.shuffle(inds)): walker i gets colour 0 when the rank of its
+// Philox key among all keys is below ceil(W/2).  Every CTA regenerates all W keys (cheap) and ranks
+// SPLIT_WALKERS of them, four threads per walker each scanning a quarter of the keys, so the
+// quadratic comparison count is spread over W / 64 CTAs (it was one CTA: 25 us at W = 1024).
+constexpr int SPLIT_WALKERS = 64;
+__global__ void __launch_bounds__(256) split_kernel(int W, uint64_t seed, const uint64_t* seed_ptr, int step,
+                                                    int32_t* __restrict__ colour) {
   extern __shared__ uint64_t keys[];
   const uint64_t sd = seed_of(seed, seed_ptr);
   for (int i = threadIdx.x; i < W; i += blockDim.x) {
@@ -28,12 +32,15 @@ __global__ void split_kernel(int W, uint64_t seed, const uint64_t* seed_ptr, int
   }
   __syncthreads();
   const int n0 = (W + 1) / 2;
-  for (int i = threadIdx.x; i < W; i += blockDim.x) {
+  const int i = blockIdx.x * SPLIT_WALKERS + (threadIdx.x >> 2), part = threadIdx.x & 3;
+  int rank = 0;
+  if (i < W) {
     const uint64_t k = keys[i];
-    int rank = 0;
-    for (int j = 0; j < W; ++j) rank += (keys[j] < k) || (keys[j] == k && j < i);
-    colour[i] = rank < n0 ? 0 : 1;
+    for (int j = part; j < W; j += 4) rank += (keys[j] < k) || (keys[j] == k && j < i);
   }
+  rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+  rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+  if (i < W && part == 0) colour[i] = rank < n0 ? 0 : 1;
 }
 
 // q_k = c - (c - s_k) z,  z = ((a-1)u+1)^2 / a,  c = random walker of the other colour;
@@ -135,9 +142,7 @@ cudaError_t prepare_mcmc() {
 
 cudaError_t launch_split(int W, uint64_t seed, const uint64_t* seed_ptr, int step, int32_t* colour,
                          cudaStream_t stream) {
-  // the rank of a key is an O(W) scan of shared memory per walker: one thread per walker up to 1024
-  const int nt = W <= 256 ? 256 : (W <= 512 ? 512 : 1024);
-  split_kernel<<<1, nt, W * sizeof(uint64_t), stream>>>(W, seed, seed_ptr, step, colour);
+  split_kernel<<<(W + SPLIT_WALKERS - 1) / SPLIT_WALKERS, 256, W * sizeof(uint64_t), stream>>>(W, seed, seed_ptr, step, colour);
   return cudaGetLastError();
 }
 cudaError_t launch_propose(const double* pos, const int32_t* colour, int W, int p, int half, double a,

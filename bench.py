@@ -490,6 +490,7 @@ def run_b200(args):
     # where the device-resident cycle goes (this rank): MCMC (graph) vs factorise + sweep + MES + argmax
     parts = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(3)]
     for i, mk in enumerate(parts):
+        barrier()            # ranks start each measured cycle together: a peer exchange waits for the slowest
         device_cycle(300 + i, marks=mk)
     barrier()
     part_mcmc = float(np.mean([mk[0].elapsed_time(mk[1]) for mk in parts]))
