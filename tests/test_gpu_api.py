@@ -372,3 +372,73 @@ def test_joint_draws_large_candidate_set_uses_the_chip_wide_factorisation(bask, 
     small = gp.sample_y(X, sample_mean=True, n_samples=4, random_state=1)
     assert big.shape == (1500, 4) and np.all(np.isfinite(big))
     np.testing.assert_allclose(big, small, atol=1e-4 * np.abs(small).max())
+
+
+def test_deferred_sample_readback_equals_eager(bask, monkeypatch):
+    """sample() returns once the MCMC graph is enqueued; chain_, pos_, theta, the acceptance fraction and a
+    sweep that gathers its theta rows on the device must be what an eager read-back gives, bit for bit."""
+    w = W.config1()
+
+    def run(eager):
+        monkeypatch.setenv("BGP_EAGER_SAMPLE", "1" if eager else "0")
+        gp = bask.BayesGPR(kernel=bask.construct_default_kernel([0, 1]), normalize_y=True, random_state=3)
+        gp.fit(w.X, w.y, noise_vector=w.noise_vector, n_desired_samples=w.n_walkers, n_burnin=2,
+               n_walkers_per_thread=w.n_walkers, progress=False)
+        gp.sample(w.X, w.y, noise_vector=w.noise_vector, n_desired_samples=3 * w.n_walkers, n_burnin=2, n_thin=2,
+                  n_walkers_per_thread=w.n_walkers)
+        assert (gp._pending is None) == eager
+        np.random.seed(5)
+        vals = bask.evaluate_acquisitions(w.candidates, gp, [bask.MaxValueSearch(), bask.ExpectedImprovement()],
+                                          n_samples=6, random_state=2)
+        assert gp._pending is None            # the sweep read the chain back behind its own kernels
+        return vals, gp.chain_.copy(), gp.pos_.copy(), gp.theta, gp._acceptance.copy(), \
+            gp.log_marginal_likelihood_value_
+
+    a, b = run(True), run(False)
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x, y)
+    assert a[1].shape == (w.n_walkers * len(range(3, 5, 2)), 4)
+
+
+def test_deferred_sample_attribute_access_and_resample(bask):
+    """Every public attribute forces the read-back; a second sample() warm-starts from the first one's walkers;
+    add=True concatenates; a rejected initial state raises although the device was already sampling."""
+    w = W.config1()
+    gp = bask.BayesGPR(kernel=bask.construct_default_kernel([0, 1]), normalize_y=True, random_state=0)
+    gp.fit(w.X, w.y, n_desired_samples=40, n_burnin=1, n_walkers_per_thread=40, progress=False)
+    gp.sample(n_desired_samples=40, n_burnin=0, n_walkers_per_thread=40)
+    assert gp._pending is not None
+    assert gp.timings_["mcmc_ms"] > 0 and gp._pending is None
+    n0 = len(gp.chain_)
+    gp.sample(n_desired_samples=40, n_burnin=0, n_walkers_per_thread=40)
+    mu, sd = gp.predict(w.candidates[:5], return_std=True)        # uses the new point estimate
+    assert gp._pending is None and np.all(np.isfinite(mu)) and np.all(sd > 0)
+    gp.sample(n_desired_samples=40, n_burnin=0, n_walkers_per_thread=40, add=True)
+    assert len(gp.chain_) == 2 * n0
+    with pytest.raises(ValueError):
+        gp.sample(n_desired_samples=40, n_burnin=0, n_walkers_per_thread=40, position=np.zeros((40, 4)))
+    assert len(gp.chain_) == 2 * n0 and gp._pending is None
+
+
+def test_identical_priors_keep_the_captured_graph(bask):
+    """bgp_set_priors with an unchanged table must not invalidate the captured MCMC graph (every sample() sets the
+    table): the second and third calls replay it -- same seed, same chain -- and are much faster to enqueue."""
+    import time
+    w = W.config1()
+    gp = bask.BayesGPR(kernel=bask.construct_default_kernel([0, 1]), normalize_y=True, random_state=0)
+    gp.fit(w.X, w.y, n_desired_samples=64, n_burnin=5, n_walkers_per_thread=64, progress=False)
+    e = gp._eng()
+    pos = gp.pos_.copy()
+    table = bask.priors.as_device_priors(bask.guess_priors(gp.kernel_), e.p)[0]
+    chains, enqueue, buf = [], [], None
+    for _ in range(3):
+        e.set_priors(table)
+        e.sync()
+        t0 = time.perf_counter()
+        buf = e.mcmc(pos, 8, 1234, buffers=buf)     # same device buffers: the graph is keyed on them
+        enqueue.append(time.perf_counter() - t0)
+        e.sync()
+        chains.append(buf["chain"].cpu().numpy().copy())
+    np.testing.assert_array_equal(chains[0], chains[1])
+    np.testing.assert_array_equal(chains[0], chains[2])
+    assert min(enqueue[1:]) < 0.5 * enqueue[0]      # capture + instantiate happen once
