@@ -248,7 +248,7 @@ class Engine:
         info = self.empty(B, dtype=torch.int32)
         check(self.lib.bgp_logprob_batched(self.h, _ptr(thetas_dev), B, _ptr(lp_extra_dev), _ptr(lp),
                                            _ptr(lml), _ptr(info), self._st), "bgp_logprob_batched")
-        self.launches += 3      # scale_x + gram + chol per wave of <= 148 thetas
+        self.launches += self._lp_launches()   # (scale_x +) gram + chol, or the fused small-n kernel, per wave
         return lp, lml, info
 
     def logprob(self, thetas, lp_extra=None):
@@ -268,7 +268,7 @@ class Engine:
         info = self.empty(S, dtype=torch.int32)
         check(self.lib.bgp_factorize_batched(self.h, _ptr(th), S, _ptr(slabs), _ptr(z), _ptr(lml),
                                              _ptr(info), self._st), "bgp_factorize_batched")
-        self.launches += 3
+        self.launches += 3 if self._lp_launches() == 3 else 2   # (scale_x +) gram + chol
         return Factor(th, slabs, z, lml, info)
 
     def extract(self, factor, index, what):
@@ -376,13 +376,18 @@ class Engine:
                                             C.c_uint64(int(seed) & (2 ** 64 - 1)), _ptr(buffers["chain"]),
                                             _ptr(buffers["lpc"]), _ptr(buffers["acc"]), self._st),
               "bgp_mcmc_run_sharded")
-        self.launches += 4 + 11 * n_steps
+        L = self._lp_launches()
+        self.launches += 1 + L + (5 + 2 * L) * n_steps   # exchange + initial log-posterior; per step as in mcmc()
         return buffers
 
     def peer_timed_out(self):
         flag = C.c_int(0)
         check(self.lib.bgp_peer_status(self.h, C.byref(flag)), "bgp_peer_status")
         return bool(flag.value)
+
+    def _lp_launches(self):
+        """Kernels per batched log-posterior wave for the current model (asked from the library)."""
+        return int(self.lib.bgp_logprob_launches(self.h))
 
     def peer_counters(self):
         """(nanoseconds spent inside peer exchanges, number of exchanges) of this rank so far."""
@@ -403,5 +408,6 @@ class Engine:
         check(self.lib.bgp_mcmc_run(self.h, _ptr(buffers["pos"]), _ptr(buffers["lp"]), W, n_steps, float(a),
                                     C.c_uint64(int(seed) & (2 ** 64 - 1)), _ptr(buffers["chain"]),
                                     _ptr(buffers["lpc"]), _ptr(buffers["acc"]), self._st), "bgp_mcmc_run")
-        self.launches += 3 + 11 * n_steps   # initial log-posterior + per step: split, 2 x (propose, 3, accept)
+        L = self._lp_launches()
+        self.launches += L + (5 + 2 * L) * n_steps   # initial log-posterior + per step: split, 2 x (propose, L, accept)
         return buffers

@@ -71,6 +71,7 @@ _SIGNATURES = {
     "bgp_peer_close": [_P],
     "bgp_peer_status": [_P, C.POINTER(C.c_int)],
     "bgp_peer_counters": [_P, C.POINTER(C.c_uint64)],
+    "bgp_logprob_launches": [_P],
     "bgp_mcmc_run_sharded": [_P, _P, _P, C.c_int, C.c_int, C.c_double, C.c_uint64, _P, _P, _P, _P],
 }
 IPC_HANDLE_BYTES = 64

@@ -202,6 +202,16 @@ static int warped(bgp_handle_t h, DevBuf& buf, const double* pts_dev, int npts, 
   return 0;
 }
 
+/* kernels one batched log-posterior call launches for the current model and data (waves of <= #SMs thetas each):
+ * 1 on the fused small-n path, 2 when the Gram kernel scales its inputs itself (default kernel shape, no input
+ * warping), else 3 (scale_x + gram + chol) -- lets a host keep an honest launch count */
+int bgp_logprob_launches(bgp_handle_t h) {
+  CHECK_H(h);
+  if (!h->have_prog || !h->have_data) return 3;
+  if (bgp::small_path_fits(h->n, h->d, h->host_prog.n_leaves)) return 1;
+  return (h->host_prog.fast_kind != 0 && h->host_prog.n_warp == 0) ? 2 : 3;
+}
+
 int bgp_set_priors(bgp_handle_t h, const bgp_prior_t* priors, int n_priors) {
   CHECK_H(h);
   CUDA_TRY(cudaSetDevice(h->device));
@@ -294,7 +304,8 @@ static int logprob_impl(bgp_handle_t h, const double* theta_dev, int batch, cons
     const int nb = batch - b0 < slots ? batch - b0 : slots;
     bgp::GramArgs Gm{h->X.as<double>(), h->alpha.as<double>(), theta_dev + (size_t)b0 * p,
                      h->slabs_scratch.as<double>(), h->xt_scratch.as<double>(), (long long)xt,
-                     h->prog.as<DevProgram>(), h->fixed_ls.as<double>(), h->n, h->d, nb, 0};
+                     h->prog.as<DevProgram>(), h->fixed_ls.as<double>(), h->n, h->d, nb, 0,
+                     h->host_prog.fast_kind != 0 && h->host_prog.n_warp == 0, h->sms};
     CUDA_TRY(bgp::launch_gram(Gm, st));
     bgp::CholArgs A;
     std::memset(&A, 0, sizeof(A));
@@ -347,7 +358,8 @@ int bgp_factorize_batched(bgp_handle_t h, const double* theta_dev, int S, double
   const size_t xt = bgp::gram_xt_doubles(h->n, h->d, h->host_prog.n_leaves);
   CUDA_TRY(h->xt_scratch.ensure(sizeof(double) * xt * (size_t)(S > slots_for(h) ? S : slots_for(h))));
   bgp::GramArgs Gm{h->X.as<double>(), h->alpha.as<double>(), theta_dev, slabs_dev, h->xt_scratch.as<double>(),
-                   (long long)xt, h->prog.as<DevProgram>(), h->fixed_ls.as<double>(), h->n, h->d, S, 1};
+                   (long long)xt, h->prog.as<DevProgram>(), h->fixed_ls.as<double>(), h->n, h->d, S, 1,
+                   h->host_prog.fast_kind != 0 && h->host_prog.n_warp == 0, h->sms};
   CUDA_TRY(bgp::launch_gram(Gm, st));
   bgp::CholArgs A;
   std::memset(&A, 0, sizeof(A));
@@ -390,7 +402,7 @@ int bgp_lml_gradient(bgp_handle_t h, const double* theta_dev, const double* alph
   CUDA_TRY(h->xt_scratch.ensure(sizeof(double) * xt * (size_t)slots_for(h)));
   CUDA_TRY(h->extract_scratch.ensure(sizeof(double) * ((size_t)h->n * h->n + bgp::grad_partial_doubles(h->n, p_kernel))));
   bgp::GramArgs Gm{h->X.as<double>(), h->alpha.as<double>(), theta_dev, nullptr, h->xt_scratch.as<double>(),
-                   (long long)xt, h->prog.as<DevProgram>(), h->fixed_ls.as<double>(), h->n, h->d, 1, 0};
+                   (long long)xt, h->prog.as<DevProgram>(), h->fixed_ls.as<double>(), h->n, h->d, 1, 0, 0, h->sms};
   CUDA_TRY(bgp::launch_scale_x(Gm, st));
   // the partial sums live behind the n x n region that bgp_factor_extract(K_INV) uses as its own scratch
   bgp::GradArgs A{h->xt_scratch.as<double>(), alpha_dev, kinv_dev, h->extract_scratch.as<double>() + (size_t)h->n * h->n,

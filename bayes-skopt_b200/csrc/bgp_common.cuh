@@ -94,17 +94,59 @@ __device__ __forceinline__ double pick_leaf(const double* r2, int leaf) {
   return v;
 }
 
+// exp(x) for finite x <= 0 and sqrt(x) for x >= 0, written for the Gram / k* inner loops: the library
+// routines spend three quarters of their issue slots on things these loops do not need (range and
+// special-case branches, register moves, constants materialised per use -- 166 instructions per
+// matrix entry of which 44 were FP64).  Here every constant is a direct constant-bank operand, there is no
+// branch, and the results stay within ~1 ulp of the library's (tools/fastmath_check.cu).
+//   exp: x = k ln2 + r (Cody-Waite, k by the 1.5 * 2^52 trick), Taylor polynomial of degree 13 in r
+//        (|r| <= ln2 / 2: remainder 4e-18), scaling by an integer add to the exponent; below -700 (1e-304,
+//        where the add would reach the denormals) the result is flushed to zero.
+//   sqrt: MUFU.RSQ64H seed, two coupled Goldschmidt iterations for sqrt(x) and 1 / (2 sqrt(x)), one
+//        residual correction; x = 0 (seed = inf) is selected at the end.
+__constant__ double BGP_EXP_TAYLOR[14] = {
+    1.0, 1.0, 0.5, 1.6666666666666666e-01, 4.1666666666666664e-02, 8.3333333333333332e-03,
+    1.3888888888888889e-03, 1.9841269841269841e-04, 2.4801587301587302e-05, 2.7557319223985893e-06,
+    2.7557319223985888e-07, 2.5052108385441720e-08, 2.0876756987868100e-09, 1.6059043836821613e-10};
+
+__device__ __forceinline__ double fast_exp_neg(double x) {
+  double kd = fma(x, 1.4426950408889634, 6755399441055744.0);
+  const int ki = __double2loint(kd);
+  kd -= 6755399441055744.0;
+  double r = fma(kd, -6.93147180369123816490e-01, x);
+  r = fma(kd, -1.90821492927058770002e-10, r);
+  double p = BGP_EXP_TAYLOR[13];
+#pragma unroll
+  for (int i = 12; i >= 0; --i) p = fma(p, r, BGP_EXP_TAYLOR[i]);
+  p = __hiloint2double(__double2hiint(p) + (ki << 20), __double2loint(p));
+  return x < -700.0 ? 0.0 : p;
+}
+
+__device__ __forceinline__ double fast_sqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double g = x * y, h = 0.5 * y;
+  double e = fma(-g, h, 0.5);
+  g = fma(g, e, g);
+  h = fma(h, e, h);
+  e = fma(-g, h, 0.5);
+  g = fma(g, e, g);
+  h = fma(h, e, h);
+  g = fma(fma(-g, g, x), h, g);
+  return x > 1e-290 ? g : 0.0;
+}
+
 __device__ __forceinline__ double stationary_value(int code, double r2) {
   if (code == BGP_OP_MATERN52) {
-    const double t = sqrt(r2) * 2.23606797749979;
-    return (1.0 + t + t * t * 0.3333333333333333) * exp(-t);
+    const double t = fast_sqrt(r2) * 2.23606797749979;
+    return (1.0 + t + t * t * 0.3333333333333333) * fast_exp_neg(-t);
   }
-  if (code == BGP_OP_RBF) return exp(-0.5 * r2);
+  if (code == BGP_OP_RBF) return fast_exp_neg(-0.5 * r2);
   if (code == BGP_OP_MATERN32) {
-    const double t = sqrt(r2) * 1.7320508075688772;
-    return (1.0 + t) * exp(-t);
+    const double t = fast_sqrt(r2) * 1.7320508075688772;
+    return (1.0 + t) * fast_exp_neg(-t);
   }
-  return exp(-sqrt(r2));
+  return fast_exp_neg(-fast_sqrt(r2));
 }
 
 __device__ __forceinline__ double eval_program(const DevProgram& P, const ThetaParams& T,

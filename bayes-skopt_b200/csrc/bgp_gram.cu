@@ -135,6 +135,72 @@ __global__ void __launch_bounds__(256, 4) gram_kernel(GramArgs A) {
   }
 }
 
+// Fast-path kernel without input warping (the default bask kernel, c * stationary(r) + white): ONE launch.
+// A CTA resolves its theta once (exp of the constant / white / length-scale entries), then walks over
+// chunks of 32 rows x 32 columns of the lower triangle: the 32 + 32 points of a chunk are scaled by the
+// inverse length scales into shared memory (coalesced read of X, 3 KB at d = 6), and every warp evaluates
+// four rows against the 32 columns from there -- no scaled copy of X in global memory, no second launch,
+// and the distance loop reads shared memory instead of waiting for L1/L2.  gridDim.x CTAs share a theta's
+// chunks round-robin (all chunks cost the same), sized so that the grid is one resident wave.
+__global__ void __launch_bounds__(256, 4) gram_fused_kernel(GramArgs A) {
+  __shared__ DevProgram PR;
+  __shared__ ThetaParams TP;
+  extern __shared__ double xs[];   // [2][d][32]: rows part, columns part
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.y, n = A.n, d = A.d;
+  {
+    const int* src = reinterpret_cast<const int*>(A.prog);
+    int* dst = reinterpret_cast<int*>(&PR);
+    for (int i = tid; i < (int)(sizeof(DevProgram) / 4); i += 256) dst[i] = src[i];
+  }
+  __syncthreads();
+  resolve_theta(PR, A.theta + (size_t)b * PR.n_theta, A.fixed_ls, TP, tid, 256);
+  __syncthreads();
+  const int fast_kind = PR.fast_kind;
+  const double cval = TP.opval[PR.fast_const], wval = TP.opval[PR.fast_white];
+  const SlabGeom G = SlabGeom::make(n, A.aug != 0);
+  const int P = (n + 31) / 32;
+  double* slab = A.slabs + (size_t)b * G.doubles();
+  constexpr int RB = GRAM_RB;
+  double* xr = xs;
+  double* xc = xs + (size_t)d * 32;
+  int k = 0, kbase = 0;   // panel of the current chunk, chunks before that panel
+  for (int chunk = blockIdx.x; ; chunk += gridDim.x) {
+    while (k < P && chunk >= kbase + gram_chunks(n, k)) { kbase += gram_chunks(n, k); ++k; }
+    if (k >= P) break;
+    const int c0 = 32 * k, R0 = c0 + GRAM_ROWS * (chunk - kbase);
+    __syncthreads();   // the previous chunk's readers are done with xs
+    for (int e = tid; e < 2 * d * 32; e += 256) {
+      const int which = e >= d * 32, j = which ? e - d * 32 : e;
+      const int i = j / d, kk = j - i * d, idx = (which ? c0 : R0) + i;
+      const double v = idx < n ? A.X[(size_t)idx * d + kk] * TP.inv_ls[0][kk] : 0.0;
+      (which ? xc : xr)[kk * 32 + i] = v;
+    }
+    __syncthreads();
+    double r2[RB];
+#pragma unroll
+    for (int a = 0; a < RB; ++a) r2[a] = 0.0;
+    for (int kk = 0; kk < d; ++kk) {
+      const double cv = xc[kk * 32 + lane];
+      const double2 r01 = *reinterpret_cast<const double2*>(xr + kk * 32 + RB * warp);
+      const double2 r23 = *reinterpret_cast<const double2*>(xr + kk * 32 + RB * warp + 2);
+      const double t0 = r01.x - cv, t1 = r01.y - cv, t2 = r23.x - cv, t3 = r23.y - cv;
+      r2[0] = fma(t0, t0, r2[0]); r2[1] = fma(t1, t1, r2[1]);
+      r2[2] = fma(t2, t2, r2[2]); r2[3] = fma(t3, t3, r2[3]);
+    }
+    const int r0 = R0 + RB * warp, col = c0 + lane;
+    double* base = slab + G.off(k);
+#pragma unroll
+    for (int a = 0; a < RB; ++a) {
+      const int row = r0 + a;
+      const bool same = row == col;
+      double v = cval * stationary_value(fast_kind, same ? 0.0 : r2[a]);
+      if (same) v += wval + A.alpha[min(row, n - 1)];
+      if (row < n && col <= row) base[(size_t)(row - c0) * 32 + lane] = v;
+    }
+  }
+}
+
 // out[s][i][kk] = warp_{theta_s}(X[i][kk]): the per-theta warped copy of a point set that the
 // sweep / posterior-covariance kernels read instead of the raw points when warping is on
 __global__ void __launch_bounds__(256) warp_points_kernel(const double* __restrict__ X, int npts, int d,
@@ -168,10 +234,17 @@ cudaError_t launch_scale_x(const GramArgs& A, cudaStream_t stream) {
 
 cudaError_t launch_gram(const GramArgs& A, cudaStream_t stream) {
   const int P = (A.n + 31) / 32;
-  cudaError_t e0 = launch_scale_x(A, stream);
-  if (e0 != cudaSuccess) return e0;
   int chunks = 0;
   for (int k = 0; k < P; ++k) chunks += gram_chunks(A.n, k);
+  if (A.fused_ok) {
+    // one resident wave: 4 CTAs per SM shared evenly by the thetas of the batch
+    int per_theta = (4 * (A.sms > 0 ? A.sms : 148)) / A.batch;
+    per_theta = per_theta < 1 ? 1 : (per_theta > chunks ? chunks : per_theta);
+    gram_fused_kernel<<<dim3(per_theta, A.batch), 256, sizeof(double) * 2 * A.d * 32, stream>>>(A);
+    return cudaGetLastError();
+  }
+  cudaError_t e0 = launch_scale_x(A, stream);
+  if (e0 != cudaSuccess) return e0;
   dim3 gg(chunks, A.batch);
   gram_kernel<<<gg, 256, 0, stream>>>(A);
   return cudaGetLastError();

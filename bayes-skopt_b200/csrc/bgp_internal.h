@@ -50,6 +50,8 @@ struct GramArgs {
   const DevProgram* prog;
   const double* fixed_ls;
   int n, d, batch, aug;
+  int fused_ok;          // host: fast-path kernel without input warping -> one launch, inputs scaled in the Gram CTAs
+  int sms;
 };
 size_t gram_xt_doubles(int n, int d, int n_leaves);
 cudaError_t launch_gram(const GramArgs& A, cudaStream_t stream);

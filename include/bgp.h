@@ -78,6 +78,10 @@ int bgp_create(bgp_handle_t* out, int device);
 int bgp_destroy(bgp_handle_t h);
 const char* bgp_last_error(void);
 int bgp_version(void);
+/* kernels one bgp_logprob_batched wave launches for the current model and data: 1 (fused small-n kernel),
+ * 2 (Gram kernel that scales its inputs + factorisation) or 3 (scale_x + Gram + factorisation); for hosts that
+ * report launch counts */
+int bgp_logprob_launches(bgp_handle_t h);
 
 /* kernel_ = user kernel (+ WhiteKernel): replaces kernel.clone_with_theta + kernel.__call__
  * (sklearn:_gpr.py:577-586).  fixed_ls: concatenated fixed ARD length scales (may be NULL). */
