@@ -5,6 +5,7 @@
 // Expectation (:197-201), LCB (:204-216), MaxValueSearch (:219-267).
 #include "bgp_common.cuh"
 #include "bgp_internal.h"
+#include "bgp_mes_table.inc"
 
 namespace bgp {
 
@@ -272,58 +273,87 @@ __global__ void mes_control_kernel(int phase, int nblk, double* __restrict__ pts
 }
 
 // mean_k [ gamma phi(gamma) / (2 Phi(gamma)) - log Phi(gamma) ],  gamma = (maxv_k + mu)/sd
-__global__ void mes_epilogue_kernel(const double* __restrict__ mu, const double* __restrict__ sd, int m,
-                                    const float* __restrict__ gumbel, int K, const double* __restrict__ fit,
-                                    double* __restrict__ out) {
-  extern __shared__ double maxv[];
-  const int s = blockIdx.y;
+//
+// A CTA sorts the K Gumbel variates of its theta once (bitonic, shared memory) and then walks over chunks of
+// 32 candidates.  With the draws in ascending order the terms of a candidate fall monotonically once
+// gamma > 1 (gamma phi(gamma) and 1 - Phi(gamma) both decrease), super-exponentially so: a lane stops as soon
+// as a term is below 1e-18 of its running sum -- everything it skips adds less than K * 1e-18 relative -- and
+// adjacent lanes (adjacent draws) take the same branch.  Non-finite rows never stop early (the comparison is
+// false for NaN / inf) and the most negative gammas, where the reference's non-finite results come from, are
+// visited first.
+constexpr int MES_EPI_THREADS = 256;
+__global__ void __launch_bounds__(MES_EPI_THREADS) mes_epilogue_kernel(
+    const double* __restrict__ mu, const double* __restrict__ sd, int m, const float* __restrict__ gumbel, int K,
+    int Kp, const double* __restrict__ fit, double* __restrict__ out) {
+  extern __shared__ float gs[];   // Kp = K rounded up to a power of two, padded with +inf
+  __shared__ double tab[BGP_MES_TAB_INTERVALS * BGP_MES_TAB_COEFS];
+  const int s = blockIdx.y, tid = threadIdx.x;
+  for (int j = tid; j < BGP_MES_TAB_INTERVALS * BGP_MES_TAB_COEFS; j += MES_EPI_THREADS) tab[j] = BGP_MES_TAB[j];
   const double alpha = fit[s * 5 + 0], beta = fit[s * 5 + 1];
-  for (int k = threadIdx.x; k < K; k += blockDim.x)
-    maxv[k] = (double)gumbel[(size_t)s * K + k] * beta + alpha;
+  for (int k = tid; k < Kp; k += MES_EPI_THREADS) gs[k] = k < K ? gumbel[(size_t)s * K + k] : INFINITY;
   __syncthreads();
+  for (int size = 2; size <= Kp; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int idx = tid; idx < Kp / 2; idx += MES_EPI_THREADS) {
+        const int lo = 2 * idx - (idx & (stride - 1)), hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        const float a = gs[lo], b = gs[hi];
+        if ((a > b) == up) { gs[lo] = b; gs[hi] = a; }
+      }
+      __syncthreads();
+    }
+  const bool sorted_up = beta > 0.0;   // maxv = beta g + alpha is ascending with g
   // a candidate's K draws are split over MES_KL adjacent lanes (more warps in flight for the long FP64
   // special-function chains), partial sums combined by a fixed shuffle tree
-  const int i = blockIdx.x * (blockDim.x / MES_KL) + threadIdx.x / MES_KL, kl = threadIdx.x % MES_KL;
-  const bool live = i < m;
-  const double mean = live ? -mu[(size_t)s * m + i] : 0.0, b = live ? sd[(size_t)s * m + i] : 1.0;
-  // one reciprocal per candidate instead of one division per draw (a division is ~20 FP64 instructions of the
-  // ~120 a term costs); gamma moves by at most an ulp.  sd = 0 (a candidate on a noise-free training point)
-  // keeps the division: 0/0 and x/0 must come out as the reference's NaN / inf
-  const double inv_b = 1.0 / b;
-  const bool use_inv = b > 1e-300 && isfinite(inv_b);
-  double acc = 0.0;
-  for (int k = kl; k < K; k += MES_KL) {
-    const double gam = use_inv ? (maxv[k] - mean) * inv_b : (maxv[k] - mean) / b;
-    double term;
-    if (gam > 0.0) {
-      // one exp shared by phi and Phi: erfc(t) = erfcx(t) exp(-t^2), phi = exp(-t^2) / sqrt(2 pi)
-      const double t = gam * 0.7071067811865476;
-      const double E = exp(-t * t);
-      const double e = 0.5 * erfcx(t) * E;                   // 1 - Phi(gamma)
-      if (e < 1e-6) {
-        // far upper tail (gamma > ~4.8, most draws of most candidates): 1/(1-e) and -log1p(-e) by their series,
-        // exact to < 1e-18 relative here -- saves the division and the log1p of the general branch
-        term = gam * 0.3989422804014327 * E * 0.5 * (1.0 + e + e * e) + e * (1.0 + e * (0.5 + e * 0.3333333333333333));
-      } else {
-        term = gam * 0.3989422804014327 * E / (2.0 * (1.0 - e)) - log1p(-e);
-      }
-    } else {
-      const double t = -gam * 0.7071067811865476;
-      if (t < 26.0) {
-        const double ex = erfcx(t);   // Phi = 0.5 ex exp(-t^2), phi = exp(-t^2)/sqrt(2 pi)
-        term = gam * 0.3989422804014327 / ex - (log(0.5 * ex) - t * t);
-      } else {
-        // the reference's naive ratio underflows here (cdf -> 0): keep its non-finite result
-        const double cdf = 0.5 * erfc(t), pdf = norm_pdf(gam);
-        term = gam * pdf / (2.0 * cdf) - (log(0.5 * erfcx(t)) - t * t);
-      }
-    }
-    acc += term;
-  }
+  const int kl = tid % MES_KL;
+  for (int base = blockIdx.x * (MES_EPI_THREADS / MES_KL); base < m; base += gridDim.x * (MES_EPI_THREADS / MES_KL)) {
+    const int i = base + tid / MES_KL;
+    const bool live = i < m;
+    const double mean = live ? -mu[(size_t)s * m + i] : 0.0, b = live ? sd[(size_t)s * m + i] : 1.0;
+    // one reciprocal per candidate instead of one division per draw; gamma moves by at most an ulp.  sd = 0 (a
+    // candidate on a noise-free training point) keeps the division: 0/0 and x/0 must come out as the
+    // reference's NaN / inf
+    const double inv_b = 1.0 / b;
+    const bool use_inv = b > 1e-300 && isfinite(inv_b);
+    double acc = 0.0;
+    for (int k = kl; k < K; k += MES_KL) {
+      const double maxv = fma((double)gs[k], beta, alpha);
+      const double gam = use_inv ? (maxv - mean) * inv_b : (maxv - mean) / b;
+      double term;
+      if (gam > 0.0) {
+        // T(gamma) = exp(-gamma^2/2) R(gamma), R by the piecewise degree-12 polynomials of bgp_mes_table.inc
+        // (relative error 2e-16, tools/gen_mes_table.py): one branch-free exp and a Horner scheme instead of
+        // exp + erfcx + a division + log1p; beyond the table exp(-gamma^2/2) has underflowed (inf * 0 keeps
+        // the NaN of an infinite gamma)
+        if (gam < 0.5 * BGP_MES_TAB_INTERVALS) {
+          const int iv = (int)(gam * 2.0);
+          const double x = fma(4.0, gam, -(double)(2 * iv + 1));
+          const double* c = tab + iv * BGP_MES_TAB_COEFS;
+          double R = c[0];
 #pragma unroll
-  for (int o = 1; o < MES_KL; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (!live || kl != 0) return;
-  out[(size_t)s * m + i] = acc / K;
+          for (int j = 1; j < BGP_MES_TAB_COEFS; ++j) R = fma(R, x, c[j]);
+          term = R * fast_exp_neg(-0.5 * gam * gam);
+        } else {
+          term = gam * 0.0;
+        }
+      } else {
+        const double t = -gam * 0.7071067811865476;
+        if (t < 26.0) {
+          const double ex = erfcx(t);   // Phi = 0.5 ex exp(-t^2), phi = exp(-t^2)/sqrt(2 pi)
+          term = gam * 0.3989422804014327 / ex - (log(0.5 * ex) - t * t);
+        } else {
+          // the reference's naive ratio underflows here (cdf -> 0): keep its non-finite result
+          const double cdf = 0.5 * erfc(t), pdf = norm_pdf(gam);
+          term = gam * pdf / (2.0 * cdf) - (log(0.5 * erfcx(t)) - t * t);
+        }
+      }
+      acc += term;
+      if (sorted_up && gam > 1.0 && term <= 1e-18 * acc) break;
+    }
+#pragma unroll
+    for (int o = 1; o < MES_KL; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (live && kl == 0) out[(size_t)s * m + i] = acc / K;
+  }
 }
 
 __global__ void finite_rows_kernel(const double* __restrict__ v, int m, const double* __restrict__ stats,
@@ -345,11 +375,11 @@ __global__ void combine_kernel(const double* __restrict__ v, int S, int m, const
   out[i] = acc;
 }
 
-// mes_epilogue_kernel keeps the K max-value draws in dynamic shared memory
-constexpr int MES_MAX_K = 24576;
+// mes_epilogue_kernel keeps the K Gumbel variates (padded to a power of two, floats) in dynamic shared memory
+constexpr int MES_MAX_K = 32768;
 cudaError_t prepare_acq() {
   return cudaFuncSetAttribute(mes_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              MES_MAX_K * (int)sizeof(double));
+                              MES_MAX_K * (int)sizeof(float));   // + 7.9 KB static for the term table
 }
 
 size_t acq_scratch_doubles(int S, int m) {
@@ -433,9 +463,16 @@ cudaError_t launch_acq_per_theta(const AcqArgs& A, cudaStream_t stream) {
       break;
     case BGP_ACQ_MES: {
       if (!A.u32 || A.K <= 0 || A.K > MES_MAX_K) return cudaErrorInvalidValue;
-      dim3 gm((m + 128 / MES_KL - 1) / (128 / MES_KL), S);
-      mes_epilogue_kernel<<<gm, 128, A.K * sizeof(double), stream>>>(A.mu, A.sd, m, A.u32, A.K,
-                                                                     A.mes_fit ? A.mes_fit : w.fit, A.per_theta);
+      int Kp = 2;
+      while (Kp < A.K) Kp <<= 1;
+      // every CTA sorts its theta's variates once, then walks over chunks of 32 candidates: about 6 CTAs per SM
+      // in all, fewer when there are not that many chunks
+      const int chunks = (m + MES_EPI_THREADS / MES_KL - 1) / (MES_EPI_THREADS / MES_KL);
+      int per_theta = (6 * 148 + S - 1) / S;
+      per_theta = per_theta > chunks ? chunks : per_theta;
+      dim3 gm(per_theta, S);
+      mes_epilogue_kernel<<<gm, MES_EPI_THREADS, Kp * sizeof(float), stream>>>(A.mu, A.sd, m, A.u32, A.K, Kp,
+                                                                              A.mes_fit ? A.mes_fit : w.fit, A.per_theta);
     } break;
     default: return cudaErrorInvalidValue;
   }

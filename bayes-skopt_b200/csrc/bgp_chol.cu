@@ -574,10 +574,19 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
       const int wrk = !overlap ? warp
                       : NW == 8 ? (warp == 0 ? -1 : warp == 4 ? 6 : warp < 4 ? warp - 1 : warp - 2)
                                 : warp - 1;
-      const int tq = T / nwk, trm = T % nwk;
-      const int mine = wrk < 0 ? 0 : tq + (wrk < trm ? 1 : 0);
-      const int w0 = wrk < 0 ? 0 : wrk * tq + min(wrk, trm);
-      const int rounds = max(1, (tq + (trm ? 1 : 0) + MAXT - 1) / MAXT);
+      // From panel HEAVY_K on the first K-loop round outlasts the potrf, which then has slack: warp 4 takes
+      // its share of the FP64 pipe of sub-partition 0 (about a sixth of the tiles -- it runs alone there, at
+      // two thirds of the issue rate of a pair) and the other six warps split the rest, extras going to the
+      // three shared sub-partitions in turn.
+      constexpr int HEAVY_K = 6;
+      const bool heavy = overlap && NW == 8 && k >= HEAVY_K;
+      const int t4 = heavy ? (T + 3) / 6 : 0;
+      const int Tr = T - t4, nwr = heavy ? nwk - 1 : nwk;
+      const int tq = Tr / nwr, trm = Tr % nwr;
+      const bool is4 = heavy && warp == 4;
+      const int mine = wrk < 0 ? 0 : is4 ? t4 : tq + (wrk < trm ? 1 : 0);
+      const int w0 = wrk < 0 ? 0 : is4 ? Tr : wrk * tq + min(wrk, trm);
+      const int rounds = max(1, (max(tq + (trm ? 1 : 0), t4) + MAXT - 1) / MAXT);
       const int per = (mine + rounds - 1) / rounds;
       for (int rd = 0; rd < rounds && wrk >= 0; ++rd) {
         const int first = w0 + rd * per;
