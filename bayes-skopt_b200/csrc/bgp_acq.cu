@@ -173,15 +173,26 @@ __global__ void mes_eval_kernel(const double* __restrict__ mu, const double* __r
                                 double* __restrict__ gpart, double* __restrict__ dpart) {
   const int s = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
   constexpr int PER = MES_CH / 256;
-  double mean[PER], sdv[PER];
+  // log Phi by the piecewise polynomials of bgp_mes_table.inc (2e-16 relative): exp(-t^2/2) R2(t) on the upper
+  // side, -t^2/2 + L(-t) on the lower side -- a branch-free exp and a Horner scheme instead of erfc + log1p /
+  // erfcx + log, and one reciprocal per candidate instead of a division per trial point
+  __shared__ double tabp[BGP_MES_TAB_INTERVALS * BGP_MES_TAB_COEFS], tabn[BGP_MES_TAB_INTERVALS * BGP_MES_TAB_COEFS];
+  for (int j = threadIdx.x; j < BGP_MES_TAB_INTERVALS * BGP_MES_TAB_COEFS; j += 256) {
+    tabp[j] = BGP_NLOGCDF_POS_TAB[j];
+    tabn[j] = BGP_LOGCDF_NEG_TAB[j];
+  }
+  double mean[PER], sdv[PER], inv[PER];
 #pragma unroll
   for (int e = 0; e < PER; ++e) {
     const int i = blk * MES_CH + e * 256 + threadIdx.x;
     if (i < m) { mean[e] = -mu[(size_t)s * m + i]; sdv[e] = sd[(size_t)s * m + i]; }
     else { mean[e] = 0.0; sdv[e] = -1.0; }   // sd < 0 marks padding
+    inv[e] = 1.0 / sdv[e];
+    if (!(sdv[e] > 1e-300 && isfinite(inv[e]))) inv[e] = 0.0;   // 0 marks "divide" (sd = 0: the reference's inf / NaN)
   }
   __shared__ double rg[8], rd[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
   // the trial points are spread over blockIdx.z in chunks of MES_PCH: with m = 10^4 a (block, theta) grid alone
   // is 200 CTAs and leaves most of the chip idle for 192 sequential points
   const int p_begin = blockIdx.z * MES_PCH, p_end = min(npts, p_begin + MES_PCH);
@@ -191,8 +202,19 @@ __global__ void mes_eval_kernel(const double* __restrict__ mu, const double* __r
 #pragma unroll
     for (int e = 0; e < PER; ++e) {
       if (sdv[e] >= 0.0) {
-        const double t = (x - mean[e]) / sdv[e];
-        g += log_ndtr(t);
+        const double t = inv[e] != 0.0 ? (x - mean[e]) * inv[e] : (x - mean[e]) / sdv[e];
+        const double u = fabs(t);
+        if (u < 0.5 * BGP_MES_TAB_INTERVALS) {
+          const int iv = (int)(u * 2.0);
+          const double xx = fma(4.0, u, -(double)(2 * iv + 1));
+          const double* c = (t >= 0.0 ? tabp : tabn) + iv * BGP_MES_TAB_COEFS;
+          double R = c[0];
+#pragma unroll
+          for (int j = 1; j < BGP_MES_TAB_COEFS; ++j) R = fma(R, xx, c[j]);
+          g += t >= 0.0 ? -R * fast_exp_neg(-0.5 * t * t) : fma(-0.5 * t, t, R);
+        } else {
+          g += log_ndtr(t);
+        }
         if (with_grad) dg += hazard_lower(t) / sdv[e];
       }
     }

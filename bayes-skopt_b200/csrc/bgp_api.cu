@@ -96,6 +96,7 @@ int bgp_create(bgp_handle_t* out, int device) {
   std::memset(&h->key, 0, sizeof(h->key));
   CUDA_TRY(bgp::prepare_mcmc());
   CUDA_TRY(bgp::prepare_acq());
+  CUDA_TRY(bgp::prepare_gram());
   CUDA_TRY(bgp::prepare_sweep());
   CUDA_TRY(bgp::prepare_small());
   CUDA_TRY(cudaMallocHost((void**)&h->seed_pinned, sizeof(uint64_t)));
@@ -209,7 +210,7 @@ int bgp_logprob_launches(bgp_handle_t h) {
   CHECK_H(h);
   if (!h->have_prog || !h->have_data) return 3;
   if (bgp::small_path_fits(h->n, h->d, h->host_prog.n_leaves)) return 1;
-  return (h->host_prog.fast_kind != 0 && h->host_prog.n_warp == 0) ? 2 : 3;
+  return (h->host_prog.fast_kind != 0 && h->host_prog.n_warp == 0 && bgp::gram_fused_fits(h->n, h->d)) ? 2 : 3;
 }
 
 int bgp_set_priors(bgp_handle_t h, const bgp_prior_t* priors, int n_priors) {

@@ -136,16 +136,21 @@ __global__ void __launch_bounds__(256, 4) gram_kernel(GramArgs A) {
 }
 
 // Fast-path kernel without input warping (the default bask kernel, c * stationary(r) + white): ONE launch.
-// A CTA resolves its theta once (exp of the constant / white / length-scale entries), then walks over
-// chunks of 32 rows x 32 columns of the lower triangle: the 32 + 32 points of a chunk are scaled by the
-// inverse length scales into shared memory (coalesced read of X, 3 KB at d = 6), and every warp evaluates
-// four rows against the 32 columns from there -- no scaled copy of X in global memory, no second launch,
-// and the distance loop reads shared memory instead of waiting for L1/L2.  gridDim.x CTAs share a theta's
-// chunks round-robin (all chunks cost the same), sized so that the grid is one resident wave.
+// A CTA resolves its theta once (exp of the constant / white / length-scale entries) and scales ALL n points by
+// the inverse length scales into shared memory, transposed ([d][n_pad]: 24 KB at n = 500, d = 6) -- no scaled
+// copy of X in global memory, no second launch, and nothing to synchronise on afterwards: the warps then walk
+// independently over a contiguous range of 32 x 32 chunks of the lower triangle, four rows per warp (four
+// independent sqrt / exp chains), lanes on the columns.  The exact-diagonal / white-noise / alpha handling
+// only exists in the diagonal chunk of a panel (a warp-uniform branch).  gridDim.x CTAs share a theta's
+// chunks, sized so that the grid is one resident wave.
+constexpr int GRAM_FUSED_MAX_SMEM = 56 * 1024;   // 4 CTAs per SM stay resident; larger problems take two launches
+__host__ __device__ inline int gram_fused_stride(int n) { return 32 * ((n + 31) / 32) + 32; }
+bool gram_fused_fits(int n, int d) { return sizeof(double) * (size_t)d * gram_fused_stride(n) <= (size_t)GRAM_FUSED_MAX_SMEM; }
+
 __global__ void __launch_bounds__(256, 4) gram_fused_kernel(GramArgs A) {
   __shared__ DevProgram PR;
   __shared__ ThetaParams TP;
-  extern __shared__ double xs[];   // [2][d][32]: rows part, columns part
+  extern __shared__ double xs[];   // [d][stride] scaled inputs, zero beyond n
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y, n = A.n, d = A.d;
   {
@@ -156,47 +161,56 @@ __global__ void __launch_bounds__(256, 4) gram_fused_kernel(GramArgs A) {
   __syncthreads();
   resolve_theta(PR, A.theta + (size_t)b * PR.n_theta, A.fixed_ls, TP, tid, 256);
   __syncthreads();
+  const int stride = gram_fused_stride(n);
+  for (int kk = 0; kk < d; ++kk) {
+    const double il = TP.inv_ls[0][kk];
+    for (int i = tid; i < stride; i += 256) xs[kk * stride + i] = i < n ? A.X[(size_t)i * d + kk] * il : 0.0;
+  }
+  __syncthreads();
   const int fast_kind = PR.fast_kind;
   const double cval = TP.opval[PR.fast_const], wval = TP.opval[PR.fast_white];
   const SlabGeom G = SlabGeom::make(n, A.aug != 0);
   const int P = (n + 31) / 32;
   double* slab = A.slabs + (size_t)b * G.doubles();
   constexpr int RB = GRAM_RB;
-  double* xr = xs;
-  double* xc = xs + (size_t)d * 32;
+  int total = 0;
+  for (int j = 0; j < P; ++j) total += gram_chunks(n, j);
+  const int first = (int)((long long)total * blockIdx.x / gridDim.x), last = (int)((long long)total * (blockIdx.x + 1) / gridDim.x);
   int k = 0, kbase = 0;   // panel of the current chunk, chunks before that panel
-  for (int chunk = blockIdx.x; ; chunk += gridDim.x) {
-    while (k < P && chunk >= kbase + gram_chunks(n, k)) { kbase += gram_chunks(n, k); ++k; }
-    if (k >= P) break;
+  for (int chunk = first; chunk < last; ++chunk) {
+    while (chunk >= kbase + gram_chunks(n, k)) { kbase += gram_chunks(n, k); ++k; }
     const int c0 = 32 * k, R0 = c0 + GRAM_ROWS * (chunk - kbase);
-    __syncthreads();   // the previous chunk's readers are done with xs
-    for (int e = tid; e < 2 * d * 32; e += 256) {
-      const int which = e >= d * 32, j = which ? e - d * 32 : e;
-      const int i = j / d, kk = j - i * d, idx = (which ? c0 : R0) + i;
-      const double v = idx < n ? A.X[(size_t)idx * d + kk] * TP.inv_ls[0][kk] : 0.0;
-      (which ? xc : xr)[kk * 32 + i] = v;
-    }
-    __syncthreads();
+    const double* xc = xs + c0 + lane;
+    const double* xr = xs + R0 + RB * warp;
     double r2[RB];
 #pragma unroll
     for (int a = 0; a < RB; ++a) r2[a] = 0.0;
     for (int kk = 0; kk < d; ++kk) {
-      const double cv = xc[kk * 32 + lane];
-      const double2 r01 = *reinterpret_cast<const double2*>(xr + kk * 32 + RB * warp);
-      const double2 r23 = *reinterpret_cast<const double2*>(xr + kk * 32 + RB * warp + 2);
+      const double cv = xc[kk * stride];
+      const double2 r01 = *reinterpret_cast<const double2*>(xr + kk * stride);
+      const double2 r23 = *reinterpret_cast<const double2*>(xr + kk * stride + 2);
       const double t0 = r01.x - cv, t1 = r01.y - cv, t2 = r23.x - cv, t3 = r23.y - cv;
       r2[0] = fma(t0, t0, r2[0]); r2[1] = fma(t1, t1, r2[1]);
       r2[2] = fma(t2, t2, r2[2]); r2[3] = fma(t3, t3, r2[3]);
     }
     const int r0 = R0 + RB * warp, col = c0 + lane;
-    double* base = slab + G.off(k);
+    double* base = slab + G.off(k) + (size_t)(r0 - c0) * 32 + lane;
+    if (R0 != c0) {
+      // strictly below the diagonal block: every column of the chunk is left of every row
 #pragma unroll
-    for (int a = 0; a < RB; ++a) {
-      const int row = r0 + a;
-      const bool same = row == col;
-      double v = cval * stationary_value(fast_kind, same ? 0.0 : r2[a]);
-      if (same) v += wval + A.alpha[min(row, n - 1)];
-      if (row < n && col <= row) base[(size_t)(row - c0) * 32 + lane] = v;
+      for (int a = 0; a < RB; ++a) {
+        const double v = cval * stationary_value(fast_kind, r2[a]);
+        if (r0 + a < n && col < n) base[a * 32] = v;
+      }
+    } else {
+#pragma unroll
+      for (int a = 0; a < RB; ++a) {
+        const int row = r0 + a;
+        const bool same = row == col;
+        double v = cval * stationary_value(fast_kind, same ? 0.0 : r2[a]);
+        if (same && row < n) v += wval + A.alpha[row];
+        if (row < n && col <= row) base[a * 32] = v;
+      }
     }
   }
 }
@@ -232,15 +246,19 @@ cudaError_t launch_scale_x(const GramArgs& A, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+cudaError_t prepare_gram() {
+  return cudaFuncSetAttribute(gram_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_FUSED_MAX_SMEM);
+}
+
 cudaError_t launch_gram(const GramArgs& A, cudaStream_t stream) {
   const int P = (A.n + 31) / 32;
   int chunks = 0;
   for (int k = 0; k < P; ++k) chunks += gram_chunks(A.n, k);
-  if (A.fused_ok) {
+  if (A.fused_ok && gram_fused_fits(A.n, A.d)) {
     // one resident wave: 4 CTAs per SM shared evenly by the thetas of the batch
     int per_theta = (4 * (A.sms > 0 ? A.sms : 148)) / A.batch;
     per_theta = per_theta < 1 ? 1 : (per_theta > chunks ? chunks : per_theta);
-    gram_fused_kernel<<<dim3(per_theta, A.batch), 256, sizeof(double) * 2 * A.d * 32, stream>>>(A);
+    gram_fused_kernel<<<dim3(per_theta, A.batch), 256, sizeof(double) * A.d * gram_fused_stride(A.n), stream>>>(A);
     return cudaGetLastError();
   }
   cudaError_t e0 = launch_scale_x(A, stream);

@@ -54,6 +54,8 @@ struct GramArgs {
   int sms;
 };
 size_t gram_xt_doubles(int n, int d, int n_leaves);
+bool gram_fused_fits(int n, int d);   // the one-launch Gram kernel keeps all scaled inputs in shared memory
+cudaError_t prepare_gram();
 cudaError_t launch_gram(const GramArgs& A, cudaStream_t stream);
 cudaError_t launch_scale_x(const GramArgs& A, cudaStream_t stream);   // the first half of launch_gram
 
