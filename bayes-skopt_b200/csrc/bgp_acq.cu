@@ -13,7 +13,7 @@ constexpr int MES_PTS = 192;      // trial points evaluated per refinement round
 constexpr int MES_CH = 512;       // candidates per block in the quantile search
 constexpr int MES_KL = 8;         // lanes that share one candidate in the MES epilogue
 constexpr int MES_PCH = 8;        // trial points per block (blockIdx.z)
-constexpr int MES_NEWTON = 6;        // quadratic from a 1/63^2 bracket: converged after 3, 6 for margin
+constexpr int MES_NEWTON = 9;        // safeguarded Newton from a 1/63 bracket: quadratic, converged after ~5
 constexpr int ST = 8;             // doubles of per-theta statistics
 constexpr int MS = 16;            // doubles of per-theta MES search state
 
@@ -190,15 +190,20 @@ __global__ void mes_eval_kernel(const double* __restrict__ mu, const double* __r
     inv[e] = 1.0 / sdv[e];
     if (!(sdv[e] > 1e-300 && isfinite(inv[e]))) inv[e] = 0.0;   // 0 marks "divide" (sd = 0: the reference's inf / NaN)
   }
-  __shared__ double rg[8], rd[8];
+  __shared__ double rg[MES_PCH][8], rd[MES_PCH][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __syncthreads();
   // the trial points are spread over blockIdx.z in chunks of MES_PCH: with m = 10^4 a (block, theta) grid alone
   // is 200 CTAs and leaves most of the chip idle for 192 sequential points
   const int p_begin = blockIdx.z * MES_PCH, p_end = min(npts, p_begin + MES_PCH);
-  for (int p = p_begin; p < p_end; ++p) {
+  // partial sums of all (<= MES_PCH) points of this CTA stay in registers; one block reduction at the end
+  double g[MES_PCH], dg[MES_PCH];
+#pragma unroll
+  for (int pp = 0; pp < MES_PCH; ++pp) {
+    g[pp] = 0.0; dg[pp] = 0.0;
+    const int p = p_begin + pp;
+    if (p >= p_end) continue;
     const double x = pts[s * MES_PTS + p];
-    double g = 0.0, dg = 0.0;
 #pragma unroll
     for (int e = 0; e < PER; ++e) {
       if (sdv[e] >= 0.0) {
@@ -211,38 +216,42 @@ __global__ void mes_eval_kernel(const double* __restrict__ mu, const double* __r
           double R = c[0];
 #pragma unroll
           for (int j = 1; j < BGP_MES_TAB_COEFS; ++j) R = fma(R, xx, c[j]);
-          g += t >= 0.0 ? -R * fast_exp_neg(-0.5 * t * t) : fma(-0.5 * t, t, R);
+          g[pp] += t >= 0.0 ? -R * fast_exp_neg(-0.5 * t * t) : fma(-0.5 * t, t, R);
         } else {
-          g += log_ndtr(t);
+          g[pp] += log_ndtr(t);
         }
-        if (with_grad) dg += hazard_lower(t) / sdv[e];
+        if (with_grad) dg[pp] += hazard_lower(t) / sdv[e];
       }
     }
-    g = warp_sum(g);
-    if (with_grad) dg = warp_sum(dg);
-    if (lane == 0) { rg[warp] = g; rd[warp] = dg; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double a = 0.0, b = 0.0;
-      for (int w = 0; w < 8; ++w) { a += rg[w]; b += rd[w]; }
-      gpart[((size_t)s * nblk + blk) * MES_PTS + p] = a;
-      if (with_grad) dpart[((size_t)s * nblk + blk) * MES_PTS + p] = b;
-    }
-    __syncthreads();
+  }
+#pragma unroll
+  for (int pp = 0; pp < MES_PCH; ++pp) {
+    g[pp] = warp_sum(g[pp]);
+    if (with_grad) dg[pp] = warp_sum(dg[pp]);
+    if (lane == 0) { rg[pp][warp] = g[pp]; rd[pp][warp] = dg[pp]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < MES_PCH && p_begin + (int)threadIdx.x < p_end) {
+    const int pp = threadIdx.x, p = p_begin + pp;
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < 8; ++w) { a += rg[pp][w]; b += rd[pp][w]; }
+    gpart[((size_t)s * nblk + blk) * MES_PTS + p] = a;
+    if (with_grad) dpart[((size_t)s * nblk + blk) * MES_PTS + p] = b;
   }
 }
 
-// phase 1: bracket on the 64-grid -> 3 x 64 refined points; phase 2: bracket again -> 3 midpoints;
-// phase 3: one safeguarded Newton step; phase 4: Gumbel fit (bask/acquisition.py:251-252)
+// phase 1: bracket the three quantiles on the 64-grid, start at the bracket midpoints; phase 3: one
+// safeguarded Newton step; phase 4: Gumbel fit (bask/acquisition.py:251-252)
 __global__ void mes_control_kernel(int phase, int nblk, double* __restrict__ pts,
                                    const double* __restrict__ gpart, const double* __restrict__ dpart,
                                    double* __restrict__ st, double* __restrict__ fit) {
   const int s = blockIdx.x, lane = threadIdx.x;
   __shared__ double g[MES_PTS], dg[4], x0[MES_PTS];
-  const int npts = phase == 1 ? 64 : (phase == 2 ? MES_PTS : 3);
+  const int npts = phase == 1 ? 64 : 3;
   for (int p = lane; p < npts; p += 32) {
     double a = 0.0, b = 0.0;
-    for (int k = 0; k < nblk; ++k) {
+#pragma unroll 8
+    for (int k = 0; k < nblk; ++k) {   // (unrolled: the loads of a group are in flight together, the order of the sum stays)
       a += gpart[((size_t)s * nblk + k) * MES_PTS + p];
       if (phase == 3) b += dpart[((size_t)s * nblk + k) * MES_PTS + p];
     }
@@ -252,26 +261,17 @@ __global__ void mes_control_kernel(int phase, int nblk, double* __restrict__ pts
   __syncwarp();
   double* S = st + s * MS;   // lo[0..2], hi[3..5], x[6..8]
   const double tau[3] = {-1.3862943611198906, -0.6931471805599453, -0.2876820724517809};
-  if (phase == 1 || phase == 2) {
+  if (phase == 1) {
     if (lane < 3) {
-      const int q = lane, base = phase == 1 ? 0 : 64 * q;
+      const int q = lane;
       int lo = 0;
-      for (int p = 0; p < 64; ++p) if (g[base + p] <= tau[q]) lo = p;   // g is non-decreasing
+      for (int p = 0; p < 64; ++p) if (g[p] <= tau[q]) lo = p;   // g is non-decreasing
       if (lo > 62) lo = 62;
-      const double xl = x0[base + lo], xh = x0[base + lo + 1];
-      S[q] = xl; S[3 + q] = xh;
-      if (phase == 2) { S[6 + q] = 0.5 * (xl + xh); }
+      const double xl = x0[lo], xh = x0[lo + 1];
+      S[q] = xl; S[3 + q] = xh; S[6 + q] = 0.5 * (xl + xh);
     }
     __syncwarp();
-    if (phase == 1) {
-      for (int p = lane; p < MES_PTS; p += 32) {
-        const int q = p >> 6, k = p & 63;
-        const double xl = S[q], xh = S[3 + q];
-        pts[s * MES_PTS + p] = k == 63 ? xh : xl + (xh - xl) * (k / 63.0);
-      }
-    } else if (lane < 3) {
-      pts[s * MES_PTS + lane] = S[6 + lane];
-    }
+    if (lane < 3) pts[s * MES_PTS + lane] = S[6 + lane];
   } else if (phase == 3) {
     if (lane < 3) {
       const int q = lane;
@@ -446,8 +446,6 @@ cudaError_t launch_mes_fit(const double* mu, const double* sd, int S, int m, dou
   auto grid = [&](int npts) { return dim3(nblk, S, (npts + MES_PCH - 1) / MES_PCH); };
   mes_eval_kernel<<<grid(64), 256, 0, stream>>>(mu, sd, m, w.pts, 64, 0, w.gpart, w.dpart);
   mes_control_kernel<<<S, 32, 0, stream>>>(1, nblk, w.pts, w.gpart, w.dpart, w.st, nullptr);
-  mes_eval_kernel<<<grid(MES_PTS), 256, 0, stream>>>(mu, sd, m, w.pts, MES_PTS, 0, w.gpart, w.dpart);
-  mes_control_kernel<<<S, 32, 0, stream>>>(2, nblk, w.pts, w.gpart, w.dpart, w.st, nullptr);
   for (int it = 0; it < MES_NEWTON; ++it) {
     mes_eval_kernel<<<grid(3), 256, 0, stream>>>(mu, sd, m, w.pts, 3, 1, w.gpart, w.dpart);
     mes_control_kernel<<<S, 32, 0, stream>>>(3, nblk, w.pts, w.gpart, w.dpart, w.st, nullptr);
