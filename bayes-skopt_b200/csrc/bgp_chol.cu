@@ -243,7 +243,8 @@ __device__ __forceinline__ void k_chunk(double (&acc)[4][4][2], const TileSet& T
           dmma(acc[t][u], h ? av[s & 1][t].y : av[s & 1][t].x, h ? bv[s & 1][u].y : bv[s & 1][u].x);
           if (i < NTL) BGP_LDS2(av[(s & 1) ^ 1][i], ring + (((s + 1) % ST) * NTL + i) * 512);
           if (i == NTL) issue(st + ST - 1, (s + ST - 1) % ST);
-          if (i > NTL && i <= NTL + 4) BGP_LDS2(bv[(s & 1) ^ 1][i - NTL - 1], bsa[i - NTL - 1] + 64 * (st + 1));
+          // (not past the last step: the columns behind the K range are being written by the block-row pushes)
+          if (i > NTL && i <= NTL + 4 && st + 1 < steps) BGP_LDS2(bv[(s & 1) ^ 1][i - NTL - 1], bsa[i - NTL - 1] + 64 * (st + 1));
           (void)c;
         }
       }
@@ -464,6 +465,8 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
     S.prog.n_ops = 0; S.prog.n_theta = 0; S.prog.n_leaves = 0; S.prog.d = 0; S.prog.fast_kind = 0;
   }
   __syncthreads();
+  // every CTA of the cluster is running before anyone stores into a peer's shared memory (the block-row pushes)
+  if (CS > 1) cluster_barrier();
   const DevProgram& PR = S.prog;
 
   for (int b = blockIdx.x / CS; b < A.batch; b += gridDim.x / CS) {
