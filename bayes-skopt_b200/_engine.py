@@ -321,7 +321,7 @@ class Engine:
                                      _ptr(per_theta), _ptr(out), _ptr(skipped), _ptr(fit), self._st),
               "bgp_acq_sweep")
         self.launches += {_lib.ACQ_EI: 4, _lib.ACQ_TTEI: 7, _lib.ACQ_MEAN: 4, _lib.ACQ_LCB: 4,
-                          _lib.ACQ_MES: 25}[kind]
+                          _lib.ACQ_MES: 15}[kind]
         return out, per_theta, skipped, fit
 
     def argmax(self, v):

@@ -166,11 +166,48 @@ __global__ void mean_lcb_kernel(const double* __restrict__ mu, const double* __r
   out[(size_t)s * m + i] = v;
 }
 
+// One safeguarded Newton step of the three quantile searches of theta s (lanes 0..2 of one warp), from the block
+// partial sums of mes_eval_kernel, summed in block order; `final`: also the Gumbel fit
+// (bask/acquisition.py:251-252).  Runs in the last CTA of a theta to finish its evaluation (the partial sums of
+// the other CTAs are read past L1).
+__device__ void mes_newton_step(int s, int nblk, int lane, double* __restrict__ pts, const double* gpart,
+                                const double* dpart, double* __restrict__ st, bool final, double* __restrict__ fit) {
+  double* S = st + s * MS;   // lo[0..2], hi[3..5], x[6..8]
+  const double tau[3] = {-1.3862943611198906, -0.6931471805599453, -0.2876820724517809};
+  if (lane < 3) {
+    const int q = lane;
+    double g = 0.0, dg = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < nblk; ++k) {
+      g += __ldcg(gpart + ((size_t)s * nblk + k) * MES_PTS + q);
+      dg += __ldcg(dpart + ((size_t)s * nblk + k) * MES_PTS + q);
+    }
+    double lo = S[q], hi = S[3 + q];
+    const double x = S[6 + q];
+    if (g <= tau[q]) lo = x; else hi = x;
+    double xn = x + (tau[q] - g) / dg;
+    if (!(xn >= lo && xn <= hi)) xn = 0.5 * (lo + hi);   // NaN or outside the bracket: bisect
+    S[q] = lo; S[3 + q] = hi; S[6 + q] = xn;
+    pts[s * MES_PTS + q] = xn;
+  }
+  __syncwarp();
+  if (final && lane == 0) {
+    const double q1 = S[6], med = S[7], q2 = S[8];
+    const double beta = (q1 - q2) / (log(log(4.0 / 3.0)) - log(log(4.0)));
+    const double alpha = med + beta * log(log(2.0));
+    S[9] = alpha; S[10] = beta;
+    if (fit) { fit[s * 5 + 0] = alpha; fit[s * 5 + 1] = beta; fit[s * 5 + 2] = q1; fit[s * 5 + 3] = med; fit[s * 5 + 4] = q2; }
+  }
+}
+
 // g(x) = sum_i log Phi((x + mu_i)/sd_i) (and optionally g') at npts trial points per theta;
 // deterministic two-stage reduction: part[s][blk][p]
+// newton: 0 = just the partial sums; 1 / 2 = the last CTA of a theta (a ticket counter per theta) also does
+// the Newton step (2: and the Gumbel fit), so a refinement round is one launch
 __global__ void mes_eval_kernel(const double* __restrict__ mu, const double* __restrict__ sd, int m,
-                                const double* __restrict__ pts, int npts, int with_grad,
-                                double* __restrict__ gpart, double* __restrict__ dpart) {
+                                double* __restrict__ pts, int npts, int with_grad,
+                                double* __restrict__ gpart, double* __restrict__ dpart, int newton,
+                                double* __restrict__ st, double* __restrict__ fit, int* __restrict__ ticket) {
   const int s = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
   constexpr int PER = MES_CH / 256;
   // log Phi by the piecewise polynomials of bgp_mes_table.inc (2e-16 relative): exp(-t^2/2) R2(t) on the upper
@@ -238,60 +275,48 @@ __global__ void mes_eval_kernel(const double* __restrict__ mu, const double* __r
     gpart[((size_t)s * nblk + blk) * MES_PTS + p] = a;
     if (with_grad) dpart[((size_t)s * nblk + blk) * MES_PTS + p] = b;
   }
+  if (newton) {   // (gridDim.z == 1 here: three points)
+    __shared__ int last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int t = atomicAdd(ticket + s, 1);
+      last = t == nblk - 1;
+      if (last) ticket[s] = 0;
+    }
+    __syncthreads();
+    if (last && warp == 0) {
+      __threadfence();
+      mes_newton_step(s, nblk, lane, pts, gpart, dpart, st, newton == 2, fit);
+    }
+  }
 }
 
-// phase 1: bracket the three quantiles on the 64-grid, start at the bracket midpoints; phase 3: one
-// safeguarded Newton step; phase 4: Gumbel fit (bask/acquisition.py:251-252)
-__global__ void mes_control_kernel(int phase, int nblk, double* __restrict__ pts,
-                                   const double* __restrict__ gpart, const double* __restrict__ dpart,
-                                   double* __restrict__ st, double* __restrict__ fit) {
+// brackets the three quantiles on the 64-point grid and starts the Newton iteration at the bracket midpoints
+__global__ void mes_bracket_kernel(int nblk, double* __restrict__ pts, const double* __restrict__ gpart,
+                                   double* __restrict__ st, int* __restrict__ ticket) {
   const int s = blockIdx.x, lane = threadIdx.x;
-  __shared__ double g[MES_PTS], dg[4], x0[MES_PTS];
-  const int npts = phase == 1 ? 64 : 3;
-  for (int p = lane; p < npts; p += 32) {
-    double a = 0.0, b = 0.0;
+  __shared__ double g[64], x0[64];
+  for (int p = lane; p < 64; p += 32) {
+    double a = 0.0;
 #pragma unroll 8
-    for (int k = 0; k < nblk; ++k) {   // (unrolled: the loads of a group are in flight together, the order of the sum stays)
-      a += gpart[((size_t)s * nblk + k) * MES_PTS + p];
-      if (phase == 3) b += dpart[((size_t)s * nblk + k) * MES_PTS + p];
-    }
+    for (int k = 0; k < nblk; ++k) a += gpart[((size_t)s * nblk + k) * MES_PTS + p];   // block order
     g[p] = a; x0[p] = pts[s * MES_PTS + p];
-    if (phase == 3) dg[p] = b;
   }
   __syncwarp();
   double* S = st + s * MS;   // lo[0..2], hi[3..5], x[6..8]
   const double tau[3] = {-1.3862943611198906, -0.6931471805599453, -0.2876820724517809};
-  if (phase == 1) {
-    if (lane < 3) {
-      const int q = lane;
-      int lo = 0;
-      for (int p = 0; p < 64; ++p) if (g[p] <= tau[q]) lo = p;   // g is non-decreasing
-      if (lo > 62) lo = 62;
-      const double xl = x0[lo], xh = x0[lo + 1];
-      S[q] = xl; S[3 + q] = xh; S[6 + q] = 0.5 * (xl + xh);
-    }
-    __syncwarp();
-    if (lane < 3) pts[s * MES_PTS + lane] = S[6 + lane];
-  } else if (phase == 3) {
-    if (lane < 3) {
-      const int q = lane;
-      double lo = S[q], hi = S[3 + q];
-      const double x = S[6 + q];
-      if (g[q] <= tau[q]) lo = x; else hi = x;
-      double xn = x + (tau[q] - g[q]) / dg[q];
-      if (!(xn >= lo && xn <= hi)) xn = 0.5 * (lo + hi);   // NaN or outside the bracket: bisect
-      S[q] = lo; S[3 + q] = hi; S[6 + q] = xn;
-      pts[s * MES_PTS + q] = xn;
-    }
-  } else {
-    if (lane == 0) {
-      const double q1 = S[6], med = S[7], q2 = S[8];
-      const double beta = (q1 - q2) / (log(log(4.0 / 3.0)) - log(log(4.0)));
-      const double alpha = med + beta * log(log(2.0));
-      S[9] = alpha; S[10] = beta;
-      if (fit) { fit[s * 5 + 0] = alpha; fit[s * 5 + 1] = beta; fit[s * 5 + 2] = q1; fit[s * 5 + 3] = med; fit[s * 5 + 4] = q2; }
-    }
+  if (lane < 3) {
+    const int q = lane;
+    int lo = 0;
+    for (int p = 0; p < 64; ++p) if (g[p] <= tau[q]) lo = p;   // g is non-decreasing
+    if (lo > 62) lo = 62;
+    const double xl = x0[lo], xh = x0[lo + 1];
+    S[q] = xl; S[3 + q] = xh; S[6 + q] = 0.5 * (xl + xh);
   }
+  __syncwarp();
+  if (lane < 3) pts[s * MES_PTS + lane] = S[6 + lane];
+  if (lane == 0) ticket[s] = 0;
 }
 
 // mean_k [ gamma phi(gamma) / (2 Phi(gamma)) - log Phi(gamma) ],  gamma = (maxv_k + mu)/sd
@@ -444,13 +469,12 @@ cudaError_t launch_mes_fit(const double* mu, const double* sd, int S, int m, dou
   AcqScratch w = carve(scratch, S, m);
   const int nblk = (m + MES_CH - 1) / MES_CH;
   auto grid = [&](int npts) { return dim3(nblk, S, (npts + MES_PCH - 1) / MES_PCH); };
-  mes_eval_kernel<<<grid(64), 256, 0, stream>>>(mu, sd, m, w.pts, 64, 0, w.gpart, w.dpart);
-  mes_control_kernel<<<S, 32, 0, stream>>>(1, nblk, w.pts, w.gpart, w.dpart, w.st, nullptr);
-  for (int it = 0; it < MES_NEWTON; ++it) {
-    mes_eval_kernel<<<grid(3), 256, 0, stream>>>(mu, sd, m, w.pts, 3, 1, w.gpart, w.dpart);
-    mes_control_kernel<<<S, 32, 0, stream>>>(3, nblk, w.pts, w.gpart, w.dpart, w.st, nullptr);
-  }
-  mes_control_kernel<<<S, 32, 0, stream>>>(4, nblk, w.pts, w.gpart, w.dpart, w.st, fit_out ? fit_out : w.fit);
+  int* ticket = reinterpret_cast<int*>(w.imax + S);   // S ints behind the S argmax slots (8 S doubles are reserved)
+  mes_eval_kernel<<<grid(64), 256, 0, stream>>>(mu, sd, m, w.pts, 64, 0, w.gpart, w.dpart, 0, nullptr, nullptr, nullptr);
+  mes_bracket_kernel<<<S, 32, 0, stream>>>(nblk, w.pts, w.gpart, w.st, ticket);
+  for (int it = 0; it < MES_NEWTON; ++it)
+    mes_eval_kernel<<<grid(3), 256, 0, stream>>>(mu, sd, m, w.pts, 3, 1, w.gpart, w.dpart, it == MES_NEWTON - 1 ? 2 : 1, w.st,
+                                                 fit_out ? fit_out : w.fit, ticket);
   return cudaGetLastError();
 }
 

@@ -279,3 +279,39 @@ def test_map_start_matches_reference(tag, name, d, g10):
     np.testing.assert_allclose(gp.log_marginal_likelihood_value_, g10[f"{tag}__map_lml"][0], rtol=1e-6)
     np.testing.assert_allclose(th, g10[f"{tag}__map_theta"], atol=2e-3)
     np.testing.assert_allclose(gp.noise_, g10[f"{tag}__map_noise"][0], rtol=5e-3)
+
+
+@pytest.mark.gpu
+def test_mes_tables_over_the_whole_gamma_range():
+    """The MES epilogue and the Gumbel fit take gamma phi/2Phi - log Phi and log Phi from piecewise polynomial
+    tables (csrc/bgp_mes_table.inc): synthetic moments that drive gamma from below zero to beyond the end of the
+    tables (38), across every interval edge, against scipy's log_ndtr form of bask/acquisition.py:236-267
+    (the fit's three quantiles must solve sum log Phi = log q; the per-theta values at 1e-10)."""
+    import torch
+    from scipy.special import log_ndtr
+    from bask_b200 import _lib
+    from bask_b200._engine import Engine
+    r = np.random.RandomState(7)
+    S, m, K = 3, 700, 257          # K not a power of two: the sort pads with +inf
+    e = Engine()
+    mu = r.uniform(-2.0, 2.0, size=(S, m))
+    sd = np.exp(r.uniform(np.log(2e-2), np.log(3.0), size=(S, m)))
+    sd[1, :5] = 1e-3                # gamma far beyond the tables for the largest max-values
+    mu[2, 0], sd[2, 0] = -10.0, 0.5  # one dominant candidate: its low max-value draws give negative gamma
+    g32 = (-np.log(-np.log(r.uniform(size=(S, K)).astype(np.float32)))).astype(np.float32)
+    out, per, skipped, fit = e.acq(_lib.ACQ_MES, e.to_dev(mu), e.to_dev(sd), gumbel32=e.to_dev(g32, dtype=torch.float32),
+                                   want_fit=True)
+    per, fit = e.to_host(per), e.to_host(fit)
+    assert (e.to_host(skipped) == 0).all()
+    for s in range(S):
+        mean = -mu[s]
+        for q, val in zip(fit[s, 2:5], (0.25, 0.5, 0.75)):
+            assert abs(np.sum(log_ndtr((q - mean) / sd[s])) - np.log(val)) < 1e-9
+        maxv = g32[s].astype(np.float64) * fit[s, 1] + fit[s, 0]
+        gam = (maxv[None, :] - mean[:, None]) / sd[s][:, None]
+        assert gam.max() > 40.0                                 # the end of the tables is exercised
+        assert s != 2 or gam.min() < -1.0                       # ... and the lower branch
+        lcdf = log_ndtr(gam)
+        ref = np.mean(gam * np.exp(-0.5 * gam * gam - 0.9189385332046727 - lcdf) / 2.0 - lcdf, axis=1)
+        np.testing.assert_allclose(per[s], ref, rtol=1e-10, atol=1e-300)
+    np.testing.assert_allclose(e.to_host(out), per.mean(axis=0), rtol=1e-13)
