@@ -377,7 +377,7 @@ class Engine:
                                             _ptr(buffers["lpc"]), _ptr(buffers["acc"]), self._st),
               "bgp_mcmc_run_sharded")
         L = self._lp_launches()
-        self.launches += 1 + L + (5 + 2 * L) * n_steps   # exchange + initial log-posterior; per step as in mcmc()
+        self.launches += 1 + L + 2 + 2 * (L + 1) * n_steps   # exchange + initial log-posterior; the rest as in mcmc()
         return buffers
 
     def peer_timed_out(self):
@@ -409,5 +409,6 @@ class Engine:
                                     C.c_uint64(int(seed) & (2 ** 64 - 1)), _ptr(buffers["chain"]),
                                     _ptr(buffers["lpc"]), _ptr(buffers["acc"]), self._st), "bgp_mcmc_run")
         L = self._lp_launches()
-        self.launches += L + (5 + 2 * L) * n_steps   # initial log-posterior + per step: split, 2 x (propose, L, accept)
+        # initial log-posterior, colours of all steps, first proposals; per half step: L + (accept + next proposals)
+        self.launches += L + 2 + 2 * (L + 1) * n_steps
         return buffers

@@ -758,29 +758,34 @@ static int mcmc_enqueue(bgp_handle_t h, double* pos, double* lp, int W, int T, d
   } else if (logprob_impl(h, pos, W, nullptr, lp, nullptr, nullptr, st)) {
     return -1;
   }
+  // colours of every step in one launch, the first proposals, then per half step: batched log-posterior of the
+  // proposals + ONE launch for the accept test and the next half step's proposals
+  if (T <= 0) return 0;
+  int32_t* colours = h->mc_colour.as<int32_t>();
+  CUDA_TRY(bgp::launch_split_all(W, T, sp, colours, st));
+  CUDA_TRY(bgp::launch_propose(pos, colours, W, p, 0, a, 0, sp, 0, h->mc_q.as<double>(), h->mc_factors.as<double>(),
+                               h->mc_movers.as<int32_t>(), st));
   for (int t = 0; t < T; ++t) {
-    CUDA_TRY(bgp::launch_split(W, 0, sp, t, h->mc_colour.as<int32_t>(), st));
     for (int half = 0; half < 2; ++half) {
       const int ns = half == 0 ? (W + 1) / 2 : W / 2;
-      CUDA_TRY(bgp::launch_propose(pos, h->mc_colour.as<int32_t>(), W, p, half, a, 0, sp, t,
-                                   h->mc_q.as<double>(), h->mc_factors.as<double>(),
-                                   h->mc_movers.as<int32_t>(), st));
       double* chain_t = (half == 1 && chain) ? chain + (size_t)t * W * p : nullptr;
       double* lpc_t = (half == 1 && lpc) ? lpc + (size_t)t * W : nullptr;
+      const int nt = half == 0 ? t : t + 1, nh = 1 - half;   // the half step after this one
+      const int32_t* next_colour = nt < T ? colours + (size_t)nt * W : nullptr;
       if (sharded) {
         shard(ns, world, rank, &lo, &cnt);
         if (cnt > 0 && logprob_impl(h, h->mc_q.as<double>() + (size_t)lo * p, cnt, nullptr, h->mc_newlp.as<double>(),
                                     nullptr, nullptr, st))
           return -1;
-        CUDA_TRY(bgp::launch_accept_xchg(h->peers, pos, lp, h->mc_q.as<double>(), h->mc_factors.as<double>(),
-                                         h->mc_newlp.as<double>(), lo, cnt, h->mc_movers.as<int32_t>(), W, p, half,
-                                         0, sp, t, acc, chain_t, lpc_t, st));
+        CUDA_TRY(bgp::launch_accept_xchg_propose(h->peers, pos, lp, h->mc_q.as<double>(), h->mc_factors.as<double>(),
+                                                 h->mc_newlp.as<double>(), lo, cnt, h->mc_movers.as<int32_t>(), W, p,
+                                                 half, sp, t, acc, chain_t, lpc_t, next_colour, nh, nt, a, st));
       } else {
         if (logprob_impl(h, h->mc_q.as<double>(), ns, nullptr, h->mc_newlp.as<double>(), nullptr, nullptr, st))
           return -1;
-        CUDA_TRY(bgp::launch_accept(pos, lp, h->mc_q.as<double>(), h->mc_factors.as<double>(),
-                                    h->mc_newlp.as<double>(), h->mc_movers.as<int32_t>(), W, p, half, 0, sp, t,
-                                    acc, chain_t, lpc_t, st));
+        CUDA_TRY(bgp::launch_accept_propose(pos, lp, h->mc_q.as<double>(), h->mc_factors.as<double>(),
+                                            h->mc_newlp.as<double>(), h->mc_movers.as<int32_t>(), W, p, half, sp, t,
+                                            acc, chain_t, lpc_t, next_colour, nh, nt, a, st));
       }
     }
   }
@@ -897,7 +902,7 @@ static int mcmc_run_impl(bgp_handle_t h, double* pos_dev, double* lp_dev, int W,
   if (h->have_priors && h->n_priors != p) return fail("prior count != theta count");
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
-  CUDA_TRY(h->mc_colour.ensure(sizeof(int32_t) * W));
+  CUDA_TRY(h->mc_colour.ensure(sizeof(int32_t) * W * (size_t)(T > 0 ? T : 1)));   // one row per step
   CUDA_TRY(h->mc_movers.ensure(sizeof(int32_t) * W));
   CUDA_TRY(h->mc_q.ensure(sizeof(double) * W * p));
   CUDA_TRY(h->mc_factors.ensure(sizeof(double) * W));

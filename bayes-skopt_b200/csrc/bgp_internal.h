@@ -204,6 +204,13 @@ cudaError_t launch_accept(double* pos, double* lp, const double* q, const double
                           uint64_t seed, const uint64_t* seed_ptr, int step, int32_t* accepted,
                           double* chain_step, double* lp_step, cudaStream_t stream);
 
+cudaError_t launch_split_all(int W, int T, const uint64_t* seed_ptr, int32_t* colour, cudaStream_t stream);
+// accept test of one half step + proposals of the next one (next_colour null: none) in one launch
+cudaError_t launch_accept_propose(double* pos, double* lp, double* q, double* factors, const double* new_lp,
+                                  int32_t* movers, int W, int p, int half, const uint64_t* seed_ptr, int step,
+                                  int32_t* accepted, double* chain_step, double* lp_step, const int32_t* next_colour,
+                                  int next_half, int next_step, double a, cudaStream_t stream);
+
 // peer exchange of walker log-probs (bgp_peer.cu): block[r] = rank r's exchange block as mapped here
 struct PeerXchg {
   double* block[8];
@@ -211,6 +218,11 @@ struct PeerXchg {
 };
 cudaError_t launch_xchg_gather(const PeerXchg& X, const double* src, int lo, int cnt, int total, double* out,
                                cudaStream_t stream);
+cudaError_t launch_accept_xchg_propose(const PeerXchg& X, double* pos, double* lp, double* q, double* factors,
+                                       const double* new_lp_local, int lo, int cnt, int32_t* movers, int W, int p,
+                                       int half, const uint64_t* seed_ptr, int step, int32_t* accepted,
+                                       double* chain_step, double* lp_step, const int32_t* next_colour, int next_half,
+                                       int next_step, double a, cudaStream_t stream);
 cudaError_t launch_accept_xchg(const PeerXchg& X, double* pos, double* lp, const double* q, const double* factors,
                                const double* new_lp_local, int lo, int cnt, const int32_t* movers, int W, int p,
                                int half, uint64_t seed, const uint64_t* seed_ptr, int step, int32_t* accepted,

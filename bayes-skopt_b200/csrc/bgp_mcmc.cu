@@ -22,10 +22,13 @@ __device__ __forceinline__ uint64_t seed_of(uint64_t seed, const uint64_t* seed_
 // SPLIT_WALKERS of them, four threads per walker each scanning a quarter of the keys, so the
 // quadratic comparison count is spread over W / 64 CTAs (it was one CTA: 25 us at W = 1024).
 constexpr int SPLIT_WALKERS = 64;
-__global__ void __launch_bounds__(256) split_kernel(int W, uint64_t seed, const uint64_t* seed_ptr, int step,
+// step0 + blockIdx.y is the step, colour + blockIdx.y * W its row: one launch can colour every step of a run
+__global__ void __launch_bounds__(256) split_kernel(int W, uint64_t seed, const uint64_t* seed_ptr, int step0,
                                                     int32_t* __restrict__ colour) {
   extern __shared__ uint64_t keys[];
   const uint64_t sd = seed_of(seed, seed_ptr);
+  const int step = step0 + blockIdx.y;
+  colour += (size_t)blockIdx.y * W;
   for (int i = threadIdx.x; i < W; i += blockDim.x) {
     Philox4 r = philox4x32_10(sd, (uint32_t)step, TAG_SPLIT, (uint32_t)i, 0u);
     keys[i] = ((uint64_t)r.c[0] << 32) | r.c[1];
@@ -45,11 +48,10 @@ __global__ void __launch_bounds__(256) split_kernel(int W, uint64_t seed, const 
 
 // q_k = c - (c - s_k) z,  z = ((a-1)u+1)^2 / a,  c = random walker of the other colour;
 // factors_k = (p-1) log z.  movers[k] = index of the k-th walker of colour `half`.
-__global__ void propose_kernel(const double* __restrict__ pos, const int32_t* __restrict__ colour, int W,
-                               int p, int half, double a, uint64_t seed, const uint64_t* seed_ptr,
-                               int step, double* __restrict__ q, double* __restrict__ factors,
-                               int32_t* __restrict__ movers) {
-  extern __shared__ int32_t lists[];   // movers[W] | others[W] | counts[2]
+__device__ void propose_body(const double* __restrict__ pos, const int32_t* __restrict__ colour, int W,
+                             int p, int half, double a, uint64_t sd, int step, double* __restrict__ q,
+                             double* __restrict__ factors, int32_t* __restrict__ movers, int32_t* lists) {
+  // lists: movers[W] | others[W] | counts[2]
   int32_t* mv = lists;
   int32_t* ot = lists + W;
   int32_t* cnt = lists + 2 * W;
@@ -80,7 +82,6 @@ __global__ void propose_kernel(const double* __restrict__ pos, const int32_t* __
     __syncthreads();
   }
   const int ns = cnt[half], nc = cnt[1 - half];
-  const uint64_t sd = seed_of(seed, seed_ptr);
   for (int k = threadIdx.x; k < ns; k += blockDim.x) {
     Philox4 r = philox4x32_10(sd, (uint32_t)step, TAG_PROP + (uint32_t)half, (uint32_t)k, 0u);
     const double u = u01_from(r.c[0], r.c[1]);
@@ -95,6 +96,14 @@ __global__ void propose_kernel(const double* __restrict__ pos, const int32_t* __
     movers[k] = mv[k];
   }
   for (int k = ns + threadIdx.x; k < W; k += blockDim.x) movers[k] = -1;
+}
+
+__global__ void propose_kernel(const double* __restrict__ pos, const int32_t* __restrict__ colour, int W,
+                               int p, int half, double a, uint64_t seed, const uint64_t* seed_ptr,
+                               int step, double* __restrict__ q, double* __restrict__ factors,
+                               int32_t* __restrict__ movers) {
+  extern __shared__ int32_t lists[];
+  propose_body(pos, colour, W, p, half, a, seed_of(seed, seed_ptr), step, q, factors, movers, lists);
 }
 
 // accept k iff factors_k + new_lp_k - lp[movers_k] > log u   (emcee RedBlueMove.propose)
@@ -130,6 +139,31 @@ __global__ void accept_kernel(double* __restrict__ pos, double* __restrict__ lp,
               lp_step);
 }
 
+// The graph of a whole run (bgp_mcmc_run) uses these instead: the accept test of half step (step, half) and the
+// proposals of the next one in ONE single-CTA launch (the colours of every step come from one split launch up
+// front), i.e. 2 T + 2 small launches per run instead of 5 T.  Same arithmetic, same Philox keys: the chain is
+// the one the separate kernels produce.
+struct NextHalf {
+  const int32_t* colour;   // row of the next half step's step; null: no further proposal
+  int half, step;
+  double a;
+};
+__global__ void accept_propose_kernel(double* __restrict__ pos, double* __restrict__ lp, double* __restrict__ q,
+                                      double* __restrict__ factors, const double* __restrict__ new_lp,
+                                      int32_t* __restrict__ movers, int W, int p, int half,
+                                      const uint64_t* seed_ptr, int step, int32_t* __restrict__ accepted,
+                                      double* __restrict__ chain_step, double* __restrict__ lp_step, NextHalf nx) {
+  extern __shared__ int32_t lists[];
+  const uint64_t sd = *seed_ptr;
+  accept_body(pos, lp, q, factors, new_lp, movers, W, p, half, sd, step, accepted, chain_step, lp_step);
+  if (nx.colour) {
+    __syncthreads();
+    propose_body(pos, nx.colour, W, p, nx.half, nx.a, sd, nx.step, q, factors, movers, lists);
+  }
+}
+
+cudaError_t prepare_mcmc_xchg();
+
 // split_kernel keeps W 64-bit sort keys in dynamic shared memory: opt in above the 48 KB default so
 // that the W <= 8192 the API accepts really launches (outside stream capture, from bgp_create)
 cudaError_t prepare_mcmc() {
@@ -137,12 +171,31 @@ cudaError_t prepare_mcmc() {
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(propose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (2 * 8192 + 2) * (int)sizeof(int32_t));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(accept_propose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (2 * 8192 + 2) * (int)sizeof(int32_t));
+  if (e == cudaSuccess) e = prepare_mcmc_xchg();
   return e;
 }
 
 cudaError_t launch_split(int W, uint64_t seed, const uint64_t* seed_ptr, int step, int32_t* colour,
                          cudaStream_t stream) {
   split_kernel<<<(W + SPLIT_WALKERS - 1) / SPLIT_WALKERS, 256, W * sizeof(uint64_t), stream>>>(W, seed, seed_ptr, step, colour);
+  return cudaGetLastError();
+}
+// colours of steps [0, T): colour[t * W + i]
+cudaError_t launch_split_all(int W, int T, const uint64_t* seed_ptr, int32_t* colour, cudaStream_t stream) {
+  if (T <= 0) return cudaSuccess;
+  split_kernel<<<dim3((W + SPLIT_WALKERS - 1) / SPLIT_WALKERS, T), 256, W * sizeof(uint64_t), stream>>>(W, 0, seed_ptr, 0, colour);
+  return cudaGetLastError();
+}
+cudaError_t launch_accept_propose(double* pos, double* lp, double* q, double* factors, const double* new_lp,
+                                  int32_t* movers, int W, int p, int half, const uint64_t* seed_ptr, int step,
+                                  int32_t* accepted, double* chain_step, double* lp_step, const int32_t* next_colour,
+                                  int next_half, int next_step, double a, cudaStream_t stream) {
+  NextHalf nx{next_colour, next_half, next_step, a};
+  accept_propose_kernel<<<1, W <= 256 ? 256 : 512, (2 * W + 2) * sizeof(int32_t), stream>>>(
+      pos, lp, q, factors, new_lp, movers, W, p, half, seed_ptr, step, accepted, chain_step, lp_step, nx);
   return cudaGetLastError();
 }
 cudaError_t launch_propose(const double* pos, const int32_t* colour, int W, int p, int half, double a,
@@ -246,6 +299,36 @@ __global__ void accept_xchg_kernel(PeerXchg X, double* __restrict__ pos, double*
   const double* new_lp = peer_exchange(X, new_lp_local, lo, cnt);
   accept_body(pos, lp, q, factors, new_lp, movers, W, p, half, seed_ptr ? *seed_ptr : seed, step, accepted,
               chain_step, lp_step);
+}
+
+__global__ void accept_xchg_propose_kernel(PeerXchg X, double* __restrict__ pos, double* __restrict__ lp,
+                                           double* __restrict__ q, double* __restrict__ factors,
+                                           const double* __restrict__ new_lp_local, int lo, int cnt,
+                                           int32_t* __restrict__ movers, int W, int p, int half,
+                                           const uint64_t* seed_ptr, int step, int32_t* __restrict__ accepted,
+                                           double* __restrict__ chain_step, double* __restrict__ lp_step, NextHalf nx) {
+  extern __shared__ int32_t lists[];
+  const uint64_t sd = *seed_ptr;
+  const double* new_lp = peer_exchange(X, new_lp_local, lo, cnt);
+  accept_body(pos, lp, q, factors, new_lp, movers, W, p, half, sd, step, accepted, chain_step, lp_step);
+  if (nx.colour) {
+    __syncthreads();
+    propose_body(pos, nx.colour, W, p, nx.half, nx.a, sd, nx.step, q, factors, movers, lists);
+  }
+}
+cudaError_t prepare_mcmc_xchg() {
+  return cudaFuncSetAttribute(accept_xchg_propose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (2 * 8192 + 2) * (int)sizeof(int32_t));
+}
+cudaError_t launch_accept_xchg_propose(const PeerXchg& X, double* pos, double* lp, double* q, double* factors,
+                                       const double* new_lp_local, int lo, int cnt, int32_t* movers, int W, int p,
+                                       int half, const uint64_t* seed_ptr, int step, int32_t* accepted,
+                                       double* chain_step, double* lp_step, const int32_t* next_colour, int next_half,
+                                       int next_step, double a, cudaStream_t stream) {
+  NextHalf nx{next_colour, next_half, next_step, a};
+  accept_xchg_propose_kernel<<<1, W <= 256 ? 256 : 512, (2 * W + 2) * sizeof(int32_t), stream>>>(
+      X, pos, lp, q, factors, new_lp_local, lo, cnt, movers, W, p, half, seed_ptr, step, accepted, chain_step, lp_step, nx);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_xchg_gather(const PeerXchg& X, const double* src, int lo, int cnt, int total, double* out,
