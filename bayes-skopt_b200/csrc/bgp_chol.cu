@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_lml_kernel(CholArgs A) {
   int crank = 0;
   if (CS > 1) asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
   const int r = lane >> 2, q = lane & 3;
-  const int n = A.n, d = A.d;
+  const int n = A.n;
   const SlabGeom G = SlabGeom::make(n, A.aug != 0);
   const int P = G.P, npad = 32 * P;
   const int kch = P - 1 < KCH ? (P - 1 > 0 ? P - 1 : 1) : KCH;

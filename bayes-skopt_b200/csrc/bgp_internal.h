@@ -223,9 +223,4 @@ cudaError_t launch_accept_xchg_propose(const PeerXchg& X, double* pos, double* l
                                        int half, const uint64_t* seed_ptr, int step, int32_t* accepted,
                                        double* chain_step, double* lp_step, const int32_t* next_colour, int next_half,
                                        int next_step, double a, cudaStream_t stream);
-cudaError_t launch_accept_xchg(const PeerXchg& X, double* pos, double* lp, const double* q, const double* factors,
-                               const double* new_lp_local, int lo, int cnt, const int32_t* movers, int W, int p,
-                               int half, uint64_t seed, const uint64_t* seed_ptr, int step, int32_t* accepted,
-                               double* chain_step, double* lp_step, cudaStream_t stream);
-
 }  // namespace bgp

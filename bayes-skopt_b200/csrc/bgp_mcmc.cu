@@ -289,18 +289,8 @@ __global__ void xchg_gather_kernel(PeerXchg X, const double* __restrict__ src, i
   for (int i = threadIdx.x; i < total; i += blockDim.x) out[i] = all[i];
 }
 
-// accept with the exchange in front: new_lp_local holds this rank's slice [lo, lo + cnt) of the half step
-__global__ void accept_xchg_kernel(PeerXchg X, double* __restrict__ pos, double* __restrict__ lp,
-                                   const double* __restrict__ q, const double* __restrict__ factors,
-                                   const double* __restrict__ new_lp_local, int lo, int cnt,
-                                   const int32_t* __restrict__ movers, int W, int p, int half, uint64_t seed,
-                                   const uint64_t* seed_ptr, int step, int32_t* __restrict__ accepted,
-                                   double* __restrict__ chain_step, double* __restrict__ lp_step) {
-  const double* new_lp = peer_exchange(X, new_lp_local, lo, cnt);
-  accept_body(pos, lp, q, factors, new_lp, movers, W, p, half, seed_ptr ? *seed_ptr : seed, step, accepted,
-              chain_step, lp_step);
-}
-
+// accept with the exchange in front (new_lp_local holds this rank's slice [lo, lo + cnt) of the half step), then
+// the next half step's proposals
 __global__ void accept_xchg_propose_kernel(PeerXchg X, double* __restrict__ pos, double* __restrict__ lp,
                                            double* __restrict__ q, double* __restrict__ factors,
                                            const double* __restrict__ new_lp_local, int lo, int cnt,
@@ -334,15 +324,6 @@ cudaError_t launch_accept_xchg_propose(const PeerXchg& X, double* pos, double* l
 cudaError_t launch_xchg_gather(const PeerXchg& X, const double* src, int lo, int cnt, int total, double* out,
                                cudaStream_t stream) {
   xchg_gather_kernel<<<1, 256, 0, stream>>>(X, src, lo, cnt, total, out);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_accept_xchg(const PeerXchg& X, double* pos, double* lp, const double* q, const double* factors,
-                               const double* new_lp_local, int lo, int cnt, const int32_t* movers, int W, int p,
-                               int half, uint64_t seed, const uint64_t* seed_ptr, int step, int32_t* accepted,
-                               double* chain_step, double* lp_step, cudaStream_t stream) {
-  accept_xchg_kernel<<<1, 256, 0, stream>>>(X, pos, lp, q, factors, new_lp_local, lo, cnt, movers, W, p, half, seed,
-                                            seed_ptr, step, accepted, chain_step, lp_step);
   return cudaGetLastError();
 }
 
