@@ -325,9 +325,9 @@ __global__ void mes_bracket_kernel(int nblk, double* __restrict__ pts, const dou
 // 32 candidates.  With the draws in ascending order the terms of a candidate fall monotonically once
 // gamma > 1 (gamma phi(gamma) and 1 - Phi(gamma) both decrease), super-exponentially so: a lane stops as soon
 // as a term is below 1e-18 of its running sum -- everything it skips adds less than K * 1e-18 relative -- and
-// adjacent lanes (adjacent draws) take the same branch.  Non-finite rows never stop early (the comparison is
-// false for NaN / inf) and the most negative gammas, where the reference's non-finite results come from, are
-// visited first.
+// adjacent lanes (adjacent draws) take the same branch.  A NaN sum never stops early (the comparison is false),
+// an infinite one stays infinite, and the most negative gammas, where the reference's non-finite results come
+// from, are visited first -- a row that is non-finite in the reference is non-finite here.
 constexpr int MES_EPI_THREADS = 256;
 __global__ void __launch_bounds__(MES_EPI_THREADS) mes_epilogue_kernel(
     const double* __restrict__ mu, const double* __restrict__ sd, int m, const float* __restrict__ gumbel, int K,
